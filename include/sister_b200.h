@@ -1,0 +1,151 @@
+/*
+ * sister_b200 -- C ABI of the B200-native (sm_100a) 5-view disparity path.
+ *
+ * This is the drop-in boundary for the hot path of CVLAB-Unibo/sister:
+ *   SisterMultiviewDisparities::compute_disparities   cpp/include/sister/SisterMultiviewDisparities.hpp:26-119
+ *     -> doMultiStereo                                hpp:152-295
+ *        -> ad_census / WTA / median / LRC / sgm      cpp/src/sister/{census,postprocess,sgm}.cpp
+ * Plain pointers and sizes only; no C++/torch types. Every entry point returns 0 or a negative
+ * SISTER_E_* code, never throws, never prints (the reference prints three timing lines per call,
+ * hpp:79,84,89, and reports errors by aborting).
+ *
+ * Terminology follows the reference: a "rig" is one set of five views (center, right, top, left,
+ * bottom -- the constructor order of hpp:22); disp_count is the reference's dispCount (number of
+ * disparity hypotheses, max disparity = disp_count - 1, hpp:155); the three outputs are
+ * disp_multiview / disp_horizontal / disp_vertical of hpp:26, CV_16UC1 H x W holding
+ * saturate_u16(disparity * 255) (hpp:111-118).
+ *
+ * There is no CPU fallback: every function that computes needs a CUDA device of compute
+ * capability 10.x and fails with SISTER_E_CUDA / SISTER_E_DEVICE otherwise.
+ */
+#ifndef SISTER_B200_H
+#define SISTER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SISTER_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+    SISTER_OK = 0,
+    SISTER_E_ARG = -1,      /* null pointer, bad channel count, bad slot ...                          */
+    SISTER_E_SHAPE = -2,    /* violates the reference's implicit preconditions (see below)             */
+    SISTER_E_CAPACITY = -3, /* larger than the max_w / max_h / max_disp given to sister_create         */
+    SISTER_E_CUDA = -4,     /* a CUDA runtime call failed; sister_last_error() has the text            */
+    SISTER_E_DEVICE = -5,   /* no usable sm_100 device                                                 */
+    SISTER_E_NOMEM = -6,    /* device or pinned-host allocation failed                                 */
+    SISTER_E_INTERNAL = -7, /* an invariant the kernels rely on was violated (reported, never silent)  */
+    SISTER_E_BUSY = -8      /* slot already has work in flight                                         */
+};
+
+/* mode_mask bits: which of the three doMultiStereo runs to perform (hpp:77,82,87). */
+#define SISTER_MODE_MULTIVIEW 1u  /* mode 0: right + left + top + bottom */
+#define SISTER_MODE_HORIZONTAL 2u /* mode 1: right + left                 */
+#define SISTER_MODE_VERTICAL 4u   /* mode 2: top + bottom                 */
+#define SISTER_MODE_ALL 7u
+
+typedef struct sister_ctx sister_ctx;
+
+/*
+ * Shape preconditions, identical to the reference's implicit ones but reported
+ * instead of crashing:   disp_count % 8 == 0   (sgm.cpp:268, postprocess.cpp:97)
+ *                        (w + 2*disp_count) % 4 == 0 and (h + 2*disp_count) % 4 == 0   (postprocess.cpp:18)
+ * Lifted limits: disp_count up to 512 (reference: < 272, postprocess.cpp:193) and 64-bit volume
+ * indexing (reference: int32, types.h:31-34).
+ */
+
+/* Create a context on CUDA device `device` able to process rigs up to max_w x max_h with up to
+ * max_disp disparities, with n_slots rigs in flight (each slot owns a stream, pinned staging and all
+ * scratch volumes: about (3 * cells + 48 * pixels) bytes, cells = (w+2D)(h+2D)D). */
+int sister_create(sister_ctx **ctx, int device, int max_w, int max_h, int max_disp, int n_slots);
+int sister_destroy(sister_ctx *ctx);
+
+/*
+ * Synchronous drop-in for compute_disparities (hpp:26) on host buffers.
+ *   views       5 pointers: center, right, top, left, bottom (hpp:22 order)
+ *   channels    3 = packed BGR as produced by cv::imread (compute_disp.cpp:19-23), converted with
+ *               OpenCV-4's fixed-point BGR2GRAY (hpp:29-33); 1 = already grey
+ *   row_stride  bytes between rows of each view (cv::Mat::step)
+ *   out         3 pointers (multiview, horizontal, vertical), each H x W uint16, dense; entries whose
+ *               mode bit is clear may be NULL and are not touched
+ *   raw_disp    optional: 3 x (h+2D) x (w+2D) int16, the un-encoded integer disparity of the whole
+ *               padded frame per mode (what WTALeft_SSE wrote at hpp:283)
+ */
+int sister_compute(sister_ctx *ctx, const uint8_t *const views[5], int w, int h, int channels,
+                   size_t row_stride, int disp_count, unsigned mode_mask, uint16_t *const out[3],
+                   int16_t *raw_disp);
+
+/* Same for n_rigs rigs (the batched / service shape of ros/README.md:31-68): views holds 5*n_rigs
+ * pointers, out 3*n_rigs. Rigs are pipelined over the context's slots: H2D copy, kernels and D2H copy
+ * of different rigs overlap. All rigs share one shape. */
+int sister_compute_batch(sister_ctx *ctx, int n_rigs, const uint8_t *const *views, int w, int h,
+                         int channels, size_t row_stride, int disp_count, unsigned mode_mask,
+                         uint16_t *const *out);
+
+/* Asynchronous halves of sister_compute for callers that pipeline themselves. */
+int sister_submit(sister_ctx *ctx, int slot, const uint8_t *const views[5], int w, int h, int channels,
+                  size_t row_stride, int disp_count, unsigned mode_mask);
+int sister_wait(sister_ctx *ctx, int slot, uint16_t *const out[3], int16_t *raw_disp);
+
+/* Device-resident variant: views_dev are device pointers (same layout as the host views, dense rows
+ * of w*channels bytes), out_dev device pointers to H x W uint16 (may be NULL per cleared mode bit).
+ * Enqueues kernels only on the slot's stream; no copies, no synchronisation. */
+int sister_submit_device(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h,
+                         int channels, int disp_count, unsigned mode_mask, uint16_t *const out_dev[3]);
+int sister_sync(sister_ctx *ctx, int slot); /* slot < 0: all slots */
+
+/* Plain device memory helpers so that a host language needs no CUDA binding of its own. */
+int sister_dev_alloc(sister_ctx *ctx, size_t bytes, void **dev_ptr);
+int sister_dev_free(sister_ctx *ctx, void *dev_ptr);
+int sister_dev_upload(sister_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes);
+int sister_dev_download(sister_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes);
+
+/* ---- measurement hooks (bench.py) ---- */
+/* Per-stage device time of the LAST submit on `slot`, measured with CUDA events on the slot's stream
+ * (enable with sister_set_profiling before submitting; adds 2 event records per stage). */
+enum {
+    SISTER_STAGE_PREP = 0,  /* grey + replicate pad + re-orientation       (hpp:29-70)        */
+    SISTER_STAGE_CENSUS,    /* 8 census maps                               (census.cpp:38-51) */
+    SISTER_STAGE_MATCH,     /* raw Hamming cost + WTA left/right, 4 views  (census.cpp:54-146, postprocess.cpp:74-315) */
+    SISTER_STAGE_MASK,      /* recursive median, LRC, confidence masks     (hpp:193-252)      */
+    SISTER_STAGE_FUSE,      /* confidence-weighted fused volume            (hpp:255-277)      */
+    SISTER_STAGE_AGGREGATE, /* SGM, both passes                            (sgm.cpp:26-455)   */
+    SISTER_STAGE_SELECT,    /* final WTA + encode/crop                     (hpp:283,111-118)  */
+    SISTER_STAGE_COUNT
+};
+int sister_set_profiling(sister_ctx *ctx, int enabled);
+int sister_get_stage_ms(sister_ctx *ctx, int slot, float *ms, int n);      /* summed over the modes run */
+int sister_get_stage_launches(sister_ctx *ctx, int slot, int *count, int n); /* kernel launches per stage, last submit */
+uint64_t sister_get_launch_count(sister_ctx *ctx);                          /* kernels launched since create */
+
+/* ---- test taps (tests/ only): copy an intermediate product of the last submit on `slot` to the host ---- */
+enum {
+    SISTER_TAP_ORIENTED = 0, /* 8 x px uint8: view-frame images, order C0,R,C180,L,C90,T,C270,B          */
+    SISTER_TAP_CENSUS,       /* 8 x px uint64: census codes of the same 8 images                          */
+    SISTER_TAP_WTA_L,        /* 4 x px int16: raw-volume WTA-left per view (right,left,top,bottom), view frame */
+    SISTER_TAP_WTA_R,        /* 4 x px int16: raw-volume WTA-right                                        */
+    SISTER_TAP_LR_FINAL,     /* 4 x px int16: left map after median + LRC (-10 = rejected), view frame    */
+    SISTER_TAP_MASKS,        /* 4 x px uint8: confidence masks in the image frame                         */
+    SISTER_TAP_FUSED,        /* cells uint8: fused volume of the LAST mode run, [row][col][d]             */
+    SISTER_TAP_SUM,          /* cells uint16: aggregated volume of the LAST mode run                      */
+    SISTER_TAP_RAW_DISP      /* 3 x px int16                                                              */
+};
+int sister_debug_fetch(sister_ctx *ctx, int slot, int what, void *host_dst, size_t bytes);
+
+/* Stage-level entry points for known-answer tests: run ONE stage on caller data (host pointers). */
+/* sgm(): fused volume uint8 [h][w][D] (values <= 252) -> aggregated uint16 [h][w][D] (sgm.cpp:457). */
+int sister_test_sgm(sister_ctx *ctx, const uint8_t *fused, int w, int h, int disp_count, uint16_t *sum,
+                    int16_t *disp /* optional WTA-left of the sum, h*w */);
+
+const char *sister_strerror(int code);
+const char *sister_last_error(sister_ctx *ctx); /* detail text of the last failure on this context */
+int sister_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SISTER_B200_H */

@@ -1,0 +1,497 @@
+// sister_b200 / api.cu -- the C ABI (include/sister_b200.h): context, slots, pipeline orchestration.
+//
+// Replaces, for the caller, SisterMultiviewDisparities::compute_disparities (hpp:26-119): staging (hpp:29-70), the
+// three doMultiStereo runs (hpp:77-89) and the output encoding (hpp:111-118). Census, per-view WTA and the
+// confidence masks are identical across the three modes (the reference recomputes them, hpp:181-252); here they are
+// computed once per rig and only fuse -> SGM -> WTA run per mode.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sister_b200.h"
+#include "kernels.cuh"
+
+using namespace sister;
+
+namespace {
+
+struct Slot {
+    cudaStream_t st = nullptr;
+    uint8_t *d_in = nullptr, *h_in = nullptr;
+    uint8_t *d_oriented = nullptr;
+    unsigned long long *d_census = nullptr;
+    int16_t *d_wtaL = nullptr, *d_wtaR = nullptr, *d_medL = nullptr, *d_medR = nullptr, *d_lr = nullptr;
+    uint8_t *d_masks = nullptr, *d_fused = nullptr;
+    uint16_t *d_sum = nullptr;
+    int16_t *d_raw = nullptr;
+    uint16_t *d_out = nullptr, *h_out = nullptr;
+    int *d_status = nullptr, *h_status = nullptr;
+    Dims dims{};
+    unsigned mode_mask = 0;
+    bool busy = false, host_io = false;
+    // profiling
+    std::vector<cudaEvent_t> ev_b, ev_e;
+    std::vector<int> ev_stage;
+    int n_ev = 0;
+    int stage_launches[SISTER_STAGE_COUNT] = {0};
+};
+
+} // namespace
+
+struct sister_ctx {
+    int device = 0;
+    int max_w = 0, max_h = 0, max_d = 0;
+    long long px_max = 0, cells_max = 0;
+    size_t in_bytes_max = 0;
+    std::vector<Slot> slots;
+    bool profiling = false;
+    LaunchCounter lc;
+    std::string err;
+};
+
+namespace {
+
+int fail_cuda(sister_ctx *ctx, cudaError_t e, const char *what)
+{
+    if (ctx) ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return (e == cudaErrorMemoryAllocation) ? SISTER_E_NOMEM : SISTER_E_CUDA;
+}
+
+#define SCK(call)                                                        \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);       \
+    } while (0)
+
+int check_shape(sister_ctx *ctx, int w, int h, int D, Dims &d)
+{
+    if (w <= 0 || h <= 0 || D <= 0) { ctx->err = "non-positive size"; return SISTER_E_ARG; }
+    if (D % 8 != 0) { ctx->err = "disp_count must be a multiple of 8 (sgm.cpp:268)"; return SISTER_E_SHAPE; }
+    if (D > 512) { ctx->err = "disp_count above 512 is not supported"; return SISTER_E_SHAPE; }
+    if ((w + 2 * D) % 4 != 0 || (h + 2 * D) % 4 != 0) { ctx->err = "(w + 2*disp_count) and (h + 2*disp_count) must be multiples of 4 (postprocess.cpp:18)"; return SISTER_E_SHAPE; }
+    if (w + 2 * D < 16 || h + 2 * D < 16) { ctx->err = "padded frame too small for the 9x7 census"; return SISTER_E_SHAPE; }
+    d.W = w; d.H = h; d.D = D; d.Wp = w + 2 * D; d.Hp = h + 2 * D;
+    d.px = (long long)d.Wp * d.Hp;
+    d.cells = d.px * D;
+    if (w > ctx->max_w || h > ctx->max_h || D > ctx->max_d || d.px > ctx->px_max || d.cells > ctx->cells_max) {
+        ctx->err = "rig larger than the capacity given to sister_create";
+        return SISTER_E_CAPACITY;
+    }
+    return SISTER_OK;
+}
+
+void begin_stage(sister_ctx *ctx, Slot &s, int stage)
+{
+    ctx->lc.cur_stage = stage;
+    if (!ctx->profiling) return;
+    if (s.n_ev == (int)s.ev_b.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        s.ev_b.push_back(a); s.ev_e.push_back(b); s.ev_stage.push_back(stage);
+    }
+    s.ev_stage[s.n_ev] = stage;
+    cudaEventRecord(s.ev_b[s.n_ev], s.st);
+}
+void end_stage(sister_ctx *ctx, Slot &s)
+{
+    if (!ctx->profiling) return;
+    cudaEventRecord(s.ev_e[s.n_ev], s.st);
+    s.n_ev++;
+}
+
+// Enqueue the whole path for one rig on the slot's stream. `in` is a device pointer to 5 views.
+int run_pipeline(sister_ctx *ctx, Slot &s, const uint8_t *const in_views[5], int row_stride, int channels, const Dims &d,
+                 unsigned mode_mask, uint16_t *const out_dev[3])
+{
+    s.n_ev = 0;
+    int before[16];
+    memcpy(before, ctx->lc.stage, sizeof(before));
+    SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
+    const unsigned view_mask = (mode_mask & SISTER_MODE_MULTIVIEW) ? 0xFu
+                               : (((mode_mask & SISTER_MODE_HORIZONTAL) ? 0x3u : 0u) | ((mode_mask & SISTER_MODE_VERTICAL) ? 0xCu : 0u));
+    // the 5 views may live anywhere on the device: express them relative to view 0 when they are equally spaced,
+    // otherwise run the prep per view group (kept simple: require equal spacing, which both callers provide)
+    const ptrdiff_t stride = in_views[1] - in_views[0];
+    for (int k = 2; k < 5; k++)
+        if (in_views[k] - in_views[k - 1] != stride) { ctx->err = "device views must be equally spaced"; return SISTER_E_ARG; }
+    if (stride <= 0) { ctx->err = "device views must be in ascending address order"; return SISTER_E_ARG; }
+
+    begin_stage(ctx, s, SISTER_STAGE_PREP);
+    launch_prep(in_views[0], (size_t)stride, row_stride, channels, d, s.d_oriented, s.st, ctx->lc);
+    end_stage(ctx, s);
+    begin_stage(ctx, s, SISTER_STAGE_CENSUS);
+    launch_census(s.d_oriented, d, s.d_census, s.st, ctx->lc);
+    end_stage(ctx, s);
+    begin_stage(ctx, s, SISTER_STAGE_MATCH);
+    launch_match_wta(s.d_census, d, view_mask, s.d_wtaL, s.d_wtaR, s.st, ctx->lc);
+    end_stage(ctx, s);
+    begin_stage(ctx, s, SISTER_STAGE_MASK);
+    launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, view_mask, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.st, ctx->lc);
+    end_stage(ctx, s);
+    for (int mode = 0; mode < 3; mode++) {
+        if (!(mode_mask & (1u << mode))) continue;
+        const unsigned vm = mode == 0 ? 0xFu : mode == 1 ? 0x3u : 0xCu; // hpp:262-276
+        begin_stage(ctx, s, SISTER_STAGE_FUSE);
+        launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused, s.d_status, s.st, ctx->lc);
+        end_stage(ctx, s);
+        begin_stage(ctx, s, SISTER_STAGE_AGGREGATE);
+        launch_sgm(s.d_fused, d, s.d_sum, s.d_status, s.st, ctx->lc);
+        end_stage(ctx, s);
+        begin_stage(ctx, s, SISTER_STAGE_SELECT);
+        launch_select(s.d_sum, d, s.d_raw + (size_t)mode * d.px, out_dev ? out_dev[mode] : nullptr, s.st, ctx->lc);
+        end_stage(ctx, s);
+    }
+    SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
+    SCK(cudaGetLastError());
+    for (int k = 0; k < SISTER_STAGE_COUNT; k++) s.stage_launches[k] = ctx->lc.stage[k] - before[k];
+    s.dims = d;
+    s.mode_mask = mode_mask;
+    return SISTER_OK;
+}
+
+void free_slot(Slot &s)
+{
+    if (s.st) cudaStreamSynchronize(s.st);
+    cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_oriented); cudaFree(s.d_census);
+    cudaFree(s.d_wtaL); cudaFree(s.d_wtaR); cudaFree(s.d_medL); cudaFree(s.d_medR); cudaFree(s.d_lr);
+    cudaFree(s.d_masks); cudaFree(s.d_fused); cudaFree(s.d_sum); cudaFree(s.d_raw); cudaFree(s.d_out);
+    cudaFreeHost(s.h_out); cudaFree(s.d_status); cudaFreeHost(s.h_status);
+    for (auto e : s.ev_b) cudaEventDestroy(e);
+    for (auto e : s.ev_e) cudaEventDestroy(e);
+    if (s.st) cudaStreamDestroy(s.st);
+    s = Slot();
+}
+
+int slot_ok(sister_ctx *ctx, int slot)
+{
+    if (!ctx) return SISTER_E_ARG;
+    if (slot < 0 || slot >= (int)ctx->slots.size()) { ctx->err = "bad slot index"; return SISTER_E_ARG; }
+    return SISTER_OK;
+}
+
+int finish_slot(sister_ctx *ctx, Slot &s)
+{
+    SCK(cudaStreamSynchronize(s.st));
+    s.busy = false;
+    if (*s.h_status != 0) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "kernel invariant violated, status bits 0x%x", *s.h_status);
+        ctx->err = buf;
+        return SISTER_E_INTERNAL;
+    }
+    return SISTER_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sister_version(void) { return SISTER_B200_VERSION; }
+
+const char *sister_strerror(int code)
+{
+    switch (code) {
+    case SISTER_OK: return "ok";
+    case SISTER_E_ARG: return "invalid argument";
+    case SISTER_E_SHAPE: return "shape violates the path's preconditions";
+    case SISTER_E_CAPACITY: return "rig exceeds the context capacity";
+    case SISTER_E_CUDA: return "CUDA error";
+    case SISTER_E_DEVICE: return "no usable sm_100 device";
+    case SISTER_E_NOMEM: return "out of memory";
+    case SISTER_E_INTERNAL: return "kernel invariant violated";
+    case SISTER_E_BUSY: return "slot busy";
+    }
+    return "unknown error";
+}
+
+const char *sister_last_error(sister_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sister_create(sister_ctx **out, int device, int max_w, int max_h, int max_disp, int n_slots)
+{
+    if (!out || max_w <= 0 || max_h <= 0 || max_disp <= 0 || n_slots <= 0 || n_slots > 64) return SISTER_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SISTER_E_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SISTER_E_DEVICE;
+    if (prop.major != 10) return SISTER_E_DEVICE; // sm_100a code only; no fallback
+    sister_ctx *ctx = new (std::nothrow) sister_ctx();
+    if (!ctx) return SISTER_E_NOMEM;
+    ctx->device = device;
+    ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_d = max_disp;
+    ctx->px_max = (long long)(max_w + 2 * max_disp) * (max_h + 2 * max_disp);
+    ctx->cells_max = ctx->px_max * max_disp;
+    ctx->in_bytes_max = (size_t)5 * max_w * max_h * 3;
+    int rc = SISTER_OK;
+    auto bail = [&](int code) { for (auto &s : ctx->slots) free_slot(s); delete ctx; return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(SISTER_E_DEVICE);
+    ctx->slots.resize(n_slots);
+    const size_t px = (size_t)ctx->px_max, cells = (size_t)ctx->cells_max, wh = (size_t)max_w * max_h;
+    for (auto &s : ctx->slots) {
+        cudaError_t e = cudaSuccess;
+        auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+        auto H = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMallocHost(p, bytes); };
+        e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking);
+        A((void **)&s.d_in, ctx->in_bytes_max); H((void **)&s.h_in, ctx->in_bytes_max);
+        A((void **)&s.d_oriented, 8 * px); A((void **)&s.d_census, 8 * px * 8);
+        A((void **)&s.d_wtaL, 4 * px * 2); A((void **)&s.d_wtaR, 4 * px * 2);
+        A((void **)&s.d_medL, 4 * px * 2); A((void **)&s.d_medR, 4 * px * 2); A((void **)&s.d_lr, 4 * px * 2);
+        A((void **)&s.d_masks, 4 * px); A((void **)&s.d_fused, cells); A((void **)&s.d_sum, cells * 2);
+        A((void **)&s.d_raw, 3 * px * 2); A((void **)&s.d_out, 3 * wh * 2); H((void **)&s.h_out, 3 * wh * 2);
+        A((void **)&s.d_status, sizeof(int)); H((void **)&s.h_status, sizeof(int));
+        if (e != cudaSuccess) { rc = fail_cuda(nullptr, e, "alloc"); return bail(rc); }
+        *s.h_status = 0;
+        cudaMemsetAsync(s.d_masks, 0, 4 * px, s.st);
+        cudaMemsetAsync(s.d_raw, 0, 3 * px * 2, s.st);
+    }
+    cudaDeviceSynchronize();
+    *out = ctx;
+    return SISTER_OK;
+}
+
+int sister_destroy(sister_ctx *ctx)
+{
+    if (!ctx) return SISTER_E_ARG;
+    cudaSetDevice(ctx->device);
+    for (auto &s : ctx->slots) free_slot(s);
+    delete ctx;
+    return SISTER_OK;
+}
+
+int sister_submit(sister_ctx *ctx, int slot, const uint8_t *const views[5], int w, int h, int channels, size_t row_stride,
+                  int disp_count, unsigned mode_mask)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    if (!views || (channels != 1 && channels != 3) || !(mode_mask & SISTER_MODE_ALL)) { ctx->err = "bad views/channels/mode_mask"; return SISTER_E_ARG; }
+    for (int k = 0; k < 5; k++) if (!views[k]) { ctx->err = "null view"; return SISTER_E_ARG; }
+    if (row_stride < (size_t)w * channels) { ctx->err = "row_stride smaller than a row"; return SISTER_E_ARG; }
+    Dims d;
+    rc = check_shape(ctx, w, h, disp_count, d);
+    if (rc) return rc;
+    Slot &s = ctx->slots[slot];
+    if (s.busy) { ctx->err = "slot busy"; return SISTER_E_BUSY; }
+    SCK(cudaSetDevice(ctx->device));
+    const size_t row = (size_t)w * channels, view_bytes = row * h;
+    for (int k = 0; k < 5; k++) {
+        uint8_t *dst = s.h_in + k * view_bytes;
+        if (row_stride == row) memcpy(dst, views[k], view_bytes);
+        else for (int i = 0; i < h; i++) memcpy(dst + i * row, views[k] + i * row_stride, row);
+    }
+    SCK(cudaMemcpyAsync(s.d_in, s.h_in, 5 * view_bytes, cudaMemcpyHostToDevice, s.st));
+    const uint8_t *dv[5];
+    for (int k = 0; k < 5; k++) dv[k] = s.d_in + k * view_bytes;
+    const size_t wh = (size_t)w * h;
+    uint16_t *od[3] = {s.d_out, s.d_out + wh, s.d_out + 2 * wh};
+    rc = run_pipeline(ctx, s, dv, (int)row, channels, d, mode_mask, od);
+    if (rc) return rc;
+    SCK(cudaMemcpyAsync(s.h_out, s.d_out, 3 * wh * 2, cudaMemcpyDeviceToHost, s.st));
+    s.busy = true;
+    s.host_io = true;
+    return SISTER_OK;
+}
+
+int sister_wait(sister_ctx *ctx, int slot, uint16_t *const out[3], int16_t *raw_disp)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    Slot &s = ctx->slots[slot];
+    if (!s.busy || !s.host_io) { ctx->err = "nothing submitted on this slot"; return SISTER_E_ARG; }
+    SCK(cudaSetDevice(ctx->device));
+    rc = finish_slot(ctx, s);
+    if (rc) return rc;
+    const size_t wh = (size_t)s.dims.W * s.dims.H;
+    for (int m = 0; m < 3; m++)
+        if ((s.mode_mask & (1u << m)) && out && out[m]) memcpy(out[m], s.h_out + m * wh, wh * 2);
+    if (raw_disp) SCK(cudaMemcpy(raw_disp, s.d_raw, (size_t)3 * s.dims.px * 2, cudaMemcpyDeviceToHost));
+    return SISTER_OK;
+}
+
+int sister_compute(sister_ctx *ctx, const uint8_t *const views[5], int w, int h, int channels, size_t row_stride,
+                   int disp_count, unsigned mode_mask, uint16_t *const out[3], int16_t *raw_disp)
+{
+    int rc = sister_submit(ctx, 0, views, w, h, channels, row_stride, disp_count, mode_mask);
+    if (rc) return rc;
+    return sister_wait(ctx, 0, out, raw_disp);
+}
+
+int sister_compute_batch(sister_ctx *ctx, int n_rigs, const uint8_t *const *views, int w, int h, int channels,
+                         size_t row_stride, int disp_count, unsigned mode_mask, uint16_t *const *out)
+{
+    if (!ctx || n_rigs < 0 || !views || !out) return SISTER_E_ARG;
+    const int ns = (int)ctx->slots.size();
+    int err = SISTER_OK;
+    std::string msg;
+    for (int k = 0; k < n_rigs && !err; k++) {
+        const int slot = k % ns;
+        if (k >= ns) err = sister_wait(ctx, slot, out + 3 * (size_t)(k - ns), nullptr); // retire the rig that held this slot
+        if (!err) err = sister_submit(ctx, slot, views + 5 * (size_t)k, w, h, channels, row_stride, disp_count, mode_mask);
+    }
+    if (err) msg = ctx->err;
+    for (int k = (n_rigs > ns ? n_rigs - ns : 0); k < n_rigs; k++) {
+        Slot &s = ctx->slots[k % ns];
+        if (!s.busy) continue;
+        if (!err) err = sister_wait(ctx, k % ns, out + 3 * (size_t)k, nullptr);
+        else { cudaStreamSynchronize(s.st); s.busy = false; } // drain after a failure
+        if (err && msg.empty()) msg = ctx->err;
+    }
+    if (err) ctx->err = msg;
+    return err;
+}
+
+int sister_submit_device(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h, int channels,
+                         int disp_count, unsigned mode_mask, uint16_t *const out_dev[3])
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    if (!views_dev || (channels != 1 && channels != 3) || !(mode_mask & SISTER_MODE_ALL)) { ctx->err = "bad views/channels/mode_mask"; return SISTER_E_ARG; }
+    Dims d;
+    rc = check_shape(ctx, w, h, disp_count, d);
+    if (rc) return rc;
+    Slot &s = ctx->slots[slot];
+    SCK(cudaSetDevice(ctx->device));
+    rc = run_pipeline(ctx, s, views_dev, w * channels, channels, d, mode_mask, out_dev);
+    if (rc) return rc;
+    s.busy = true;
+    s.host_io = false;
+    return SISTER_OK;
+}
+
+int sister_sync(sister_ctx *ctx, int slot)
+{
+    if (!ctx) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    int rc = SISTER_OK;
+    for (int k = 0; k < (int)ctx->slots.size(); k++) {
+        if (slot >= 0 && k != slot) continue;
+        Slot &s = ctx->slots[k];
+        int r = finish_slot(ctx, s);
+        if (r && !rc) rc = r;
+    }
+    return rc;
+}
+
+int sister_dev_alloc(sister_ctx *ctx, size_t bytes, void **dev_ptr)
+{
+    if (!ctx || !dev_ptr) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    SCK(cudaMalloc(dev_ptr, bytes));
+    return SISTER_OK;
+}
+int sister_dev_free(sister_ctx *ctx, void *dev_ptr)
+{
+    if (!ctx) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    SCK(cudaFree(dev_ptr));
+    return SISTER_OK;
+}
+int sister_dev_upload(sister_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes)
+{
+    if (!ctx) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    SCK(cudaMemcpy(dev_dst, host_src, bytes, cudaMemcpyHostToDevice));
+    return SISTER_OK;
+}
+int sister_dev_download(sister_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes)
+{
+    if (!ctx) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    SCK(cudaMemcpy(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost));
+    return SISTER_OK;
+}
+
+int sister_set_profiling(sister_ctx *ctx, int enabled)
+{
+    if (!ctx) return SISTER_E_ARG;
+    ctx->profiling = enabled != 0;
+    return SISTER_OK;
+}
+
+int sister_get_stage_ms(sister_ctx *ctx, int slot, float *ms, int n)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    if (!ms || n < SISTER_STAGE_COUNT) return SISTER_E_ARG;
+    Slot &s = ctx->slots[slot];
+    SCK(cudaSetDevice(ctx->device));
+    SCK(cudaStreamSynchronize(s.st));
+    for (int k = 0; k < n; k++) ms[k] = 0.f;
+    for (int k = 0; k < s.n_ev; k++) {
+        float t = 0.f;
+        SCK(cudaEventElapsedTime(&t, s.ev_b[k], s.ev_e[k]));
+        ms[s.ev_stage[k]] += t;
+    }
+    return SISTER_OK;
+}
+
+int sister_get_stage_launches(sister_ctx *ctx, int slot, int *count, int n)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    if (!count || n < SISTER_STAGE_COUNT) return SISTER_E_ARG;
+    for (int k = 0; k < SISTER_STAGE_COUNT; k++) count[k] = ctx->slots[slot].stage_launches[k];
+    return SISTER_OK;
+}
+
+uint64_t sister_get_launch_count(sister_ctx *ctx) { return ctx ? ctx->lc.total : 0; }
+
+int sister_debug_fetch(sister_ctx *ctx, int slot, int what, void *host_dst, size_t bytes)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    if (!host_dst) return SISTER_E_ARG;
+    Slot &s = ctx->slots[slot];
+    SCK(cudaSetDevice(ctx->device));
+    SCK(cudaStreamSynchronize(s.st));
+    const size_t px = (size_t)s.dims.px, cells = (size_t)s.dims.cells;
+    const void *src = nullptr;
+    size_t have = 0;
+    switch (what) {
+    case SISTER_TAP_ORIENTED: src = s.d_oriented; have = 8 * px; break;
+    case SISTER_TAP_CENSUS: src = s.d_census; have = 8 * px * 8; break;
+    case SISTER_TAP_WTA_L: src = s.d_wtaL; have = 4 * px * 2; break;
+    case SISTER_TAP_WTA_R: src = s.d_wtaR; have = 4 * px * 2; break;
+    case SISTER_TAP_LR_FINAL: src = s.d_lr; have = 4 * px * 2; break;
+    case SISTER_TAP_MASKS: src = s.d_masks; have = 4 * px; break;
+    case SISTER_TAP_FUSED: src = s.d_fused; have = cells; break;
+    case SISTER_TAP_SUM: src = s.d_sum; have = cells * 2; break;
+    case SISTER_TAP_RAW_DISP: src = s.d_raw; have = 3 * px * 2; break;
+    default: ctx->err = "unknown tap"; return SISTER_E_ARG;
+    }
+    if (bytes > have) { ctx->err = "tap smaller than requested"; return SISTER_E_ARG; }
+    SCK(cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost));
+    return SISTER_OK;
+}
+
+int sister_test_sgm(sister_ctx *ctx, const uint8_t *fused, int w, int h, int disp_count, uint16_t *sum, int16_t *disp)
+{
+    if (!ctx || !fused || !sum) return SISTER_E_ARG;
+    if (disp_count <= 0 || disp_count % 2 != 0 || disp_count > 512 || w < 2 || h < 2) { ctx->err = "bad sgm test shape"; return SISTER_E_SHAPE; }
+    Dims d;
+    d.W = 0; d.H = 0; d.D = disp_count; d.Wp = w; d.Hp = h;
+    d.px = (long long)w * h;
+    d.cells = d.px * disp_count;
+    if (d.px > ctx->px_max || d.cells > ctx->cells_max) { ctx->err = "sgm test volume exceeds capacity"; return SISTER_E_CAPACITY; }
+    Slot &s = ctx->slots[0];
+    if (s.busy) return SISTER_E_BUSY;
+    SCK(cudaSetDevice(ctx->device));
+    SCK(cudaMemcpyAsync(s.d_fused, fused, (size_t)d.cells, cudaMemcpyHostToDevice, s.st));
+    SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
+    ctx->lc.cur_stage = SISTER_STAGE_AGGREGATE;
+    launch_sgm(s.d_fused, d, s.d_sum, s.d_status, s.st, ctx->lc);
+    ctx->lc.cur_stage = SISTER_STAGE_SELECT;
+    launch_select(s.d_sum, d, s.d_raw, nullptr, s.st, ctx->lc);
+    SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
+    SCK(cudaGetLastError());
+    SCK(cudaStreamSynchronize(s.st));
+    SCK(cudaMemcpy(sum, s.d_sum, (size_t)d.cells * 2, cudaMemcpyDeviceToHost));
+    if (disp) SCK(cudaMemcpy(disp, s.d_raw, (size_t)d.px * 2, cudaMemcpyDeviceToHost));
+    s.dims = d;
+    return *s.h_status ? SISTER_E_INTERNAL : SISTER_OK;
+}
+
+} // extern "C"

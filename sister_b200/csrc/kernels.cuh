@@ -1,0 +1,38 @@
+// Host-side launch wrappers of the sm_100a kernels (definitions in stage.cu / match.cu / sgm.cu).
+#pragma once
+#include "common.cuh"
+
+namespace sister {
+
+struct LaunchCounter {
+    unsigned long long total = 0;
+    int stage[16] = {0};
+    int cur_stage = 0;
+    inline void add(int n = 1) { total += n; stage[cur_stage] += n; }
+};
+
+// ---- stage.cu ----
+// grey + replicate pad + re-orientation: 5 input views -> 8 oriented view-frame images (hpp:29-70)
+void launch_prep(const uint8_t *in, size_t view_stride, int row_stride, int channels, const Dims &d,
+                 uint8_t *oriented, cudaStream_t st, LaunchCounter &lc);
+// 9x7 centre-symmetric census with the bit-63 carry, on the 8 oriented images (census.cpp:30-51)
+void launch_census(const uint8_t *oriented, const Dims &d, unsigned long long *census, cudaStream_t st, LaunchCounter &lc);
+
+// ---- match.cu ----
+// raw Hamming cost + WTA-left + WTA-right for the views in view_mask (census.cpp:54-146, postprocess.cpp:74-315)
+void launch_match_wta(const unsigned long long *census, const Dims &d, unsigned view_mask, int16_t *wtaL, int16_t *wtaR,
+                      cudaStream_t st, LaunchCounter &lc);
+// in-place-semantics 3x3 median (postprocess.cpp:15-71 with src == dst), LRC (postprocess.cpp:318-341), masks (hpp:201-251)
+void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims &d, unsigned view_mask, int16_t *medL,
+                            int16_t *medR, int16_t *lr_final, uint8_t *masks, cudaStream_t st, LaunchCounter &lc);
+// fused volume C = sum_v mask_v * cost_v as uint8 (hpp:255-277); view_mask selects the mode's views
+void launch_fuse(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
+                 int *status, cudaStream_t st, LaunchCounter &lc);
+
+// ---- sgm.cu ----
+// 8-path SGM (sgm.cpp:26-455) on the uint8 fused volume -> uint16 sum volume
+void launch_sgm(const uint8_t *fused, const Dims &d, uint16_t *sum, int *status, cudaStream_t st, LaunchCounter &lc);
+// final WTA-left (hpp:283) + convertTo/crop/*255 (hpp:111-118)
+void launch_select(const uint16_t *sum, const Dims &d, int16_t *raw_disp, uint16_t *out, cudaStream_t st, LaunchCounter &lc);
+
+} // namespace sister

@@ -1,0 +1,153 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
+Everything here is bit-exact: the whole path is integer (the reference has no sub-pixel step, postprocess.cpp:141)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_rigs
+from sister_b200.synth import make_rig
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import sister_b200
+    if not os.path.exists(sister_b200.library_path()):
+        sister_b200.build_library()
+    eng = sister_b200.Engine(256, 256, 64, n_slots=3)
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("name", golden_rigs())
+def test_golden_rigs(engine, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    w, h, D = int(g["w"]), int(g["h"]), int(g["D"])
+    views = make_rig(w, h, D, seed=int(g["seed"]), kind=str(g["kind"]), channels=3)
+    outs, raw = engine.compute(views, D, want_raw=True)
+    for m, key in enumerate(("disp_mv", "disp_h", "disp_v")):
+        assert (raw[m] == g[f"raw_disp_m{m}"]).all(), f"raw disparity differs, mode {m}: {(raw[m] != g[f'raw_disp_m{m}']).sum()} px"
+        assert (outs[m] == g[key]).all(), key
+    # grey input == grey replicated to BGR; single mode leaves the other outputs untouched
+    outs1 = engine.compute([v[:, :, 0] for v in views], D, mode_mask=1)
+    assert (outs1[0] == g["disp_mv"]).all() and outs1[1] is None and outs1[2] is None
+    outs2 = engine.compute(views, D, mode_mask=6)
+    assert outs2[0] is None and (outs2[1] == g["disp_h"]).all() and (outs2[2] == g["disp_v"]).all()
+
+
+@pytest.mark.parametrize("w,h,D,kind,seed", [(96, 64, 32, "smooth", 11), (40, 56, 8, "plane", 12), (72, 60, 24, "smooth", 13)])
+def test_every_stage_against_oracle(engine, oracle_lib, w, h, D, kind, seed):
+    views = make_rig(w, h, D, seed=seed, kind=kind, channels=3)
+    wp, hp = w + 2 * D, h + 2 * D
+    px = wp * hp
+    pads = [oracle_lib.pad_replicate(oracle_lib.grey_bgr(v), D) for v in views]
+    rots = (0, 180, 90, 270)
+    side = (1, 3, 2, 4)
+    for mode in (2, 1, 0):
+        engine.compute(views, D, mode_mask=1 << mode)
+        t = oracle_lib.multistereo(pads, D, mode)
+        fused = engine.fetch("fused", (hp, wp, D), np.uint8)
+        assert (fused == t["fused"]).all(), f"fused volume, mode {mode}"
+        ssum = engine.fetch("sum", (hp, wp, D), np.uint16)
+        assert (ssum == t["sum"]).all(), f"aggregated volume, mode {mode}: {(ssum != t['sum']).sum()} cells"
+        raw = engine.fetch("raw_disp", (3, hp, wp), np.int16)
+        assert (raw[mode] == t["disp"]).all()
+    # after mode 0 all four views were matched: compare the per-view products
+    ori = engine.fetch("oriented", (8, px), np.uint8)
+    cen = engine.fetch("census", (8, px), np.uint64)
+    wl = engine.fetch("wta_l", (4, px), np.int16)
+    wr = engine.fetch("wta_r", (4, px), np.int16)
+    lr = engine.fetch("lr_final", (4, px), np.int16)
+    masks = engine.fetch("masks", (4, hp, wp), np.uint8)
+    for v in range(4):
+        c_img = oracle_lib.orient(pads[0], rots[v])
+        s_img = oracle_lib.orient(pads[side[v]], rots[v])
+        assert (ori[2 * v] == c_img.ravel()).all() and (ori[2 * v + 1] == s_img.ravel()).all(), f"oriented images, view {v}"
+        c1, c2 = oracle_lib.census(c_img), oracle_lib.census(s_img)
+        assert (cen[2 * v] == c1.ravel()).all() and (cen[2 * v + 1] == c2.ravel()).all(), f"census, view {v}"
+        L, R = oracle_lib.wta(oracle_lib.cost_volume(c1, c2, D))
+        assert (wl[v] == L.ravel()).all(), f"WTA-left, view {v}"
+        assert (wr[v] == R.ravel()).all(), f"WTA-right, view {v}"
+        assert (lr[v] == t["lr"][v]).all(), f"median + LRC, view {v}"
+    assert (masks == t["masks"]).all()
+
+
+def test_sgm_known_answers(engine, oracle_lib):
+    k = np.load(os.path.join(GOLDEN, "stage_kats.npz"))
+    for i in range(3):
+        s, disp = engine.test_sgm(k[f"sgm8_in_{i}"])
+        assert (s == k[f"sgm8_out_{i}"]).all(), f"KAT {i}"
+    rng = np.random.default_rng(99)
+    for (h, w, D) in [(40, 52, 16), (36, 88, 32), (24, 40, 8), (30, 44, 72), (20, 36, 200), (16, 24, 136), (12, 20, 512)]:
+        vol = rng.integers(0, 253, (h, w, D), dtype=np.uint8)
+        vol[rng.random((h, w, D)) < 0.2] = 0
+        s, disp = engine.test_sgm(vol)
+        ref = oracle_lib.sgm(vol.astype(np.uint16))
+        assert (s == ref).all(), f"SGM {h}x{w}x{D}: {(s != ref).sum()} cells differ"
+        L, _ = oracle_lib.wta(ref)
+        assert (disp == L).all(), f"final WTA {h}x{w}x{D}"
+
+
+def test_shape_preconditions_are_reported(engine):
+    import sister_b200
+    views = make_rig(64, 48, 16, channels=1)
+    for bad_d in (12, 20):
+        with pytest.raises(sister_b200.SisterError) as e:
+            engine.compute(views, bad_d)
+        assert e.value.code == -2
+    with pytest.raises(sister_b200.SisterError) as e:
+        engine.compute(make_rig(62, 48, 16, channels=1), 16)  # (w + 2D) % 4 != 0 (postprocess.cpp:18)
+    assert e.value.code == -2
+    with pytest.raises(sister_b200.SisterError) as e:
+        engine.compute(make_rig(512, 48, 16, channels=1), 16)
+    assert e.value.code == -3
+
+
+def test_batch_equals_single_and_is_deterministic(engine):
+    rigs = [make_rig(96, 64, 32, seed=100 + k, channels=1) for k in range(7)]
+    single = [engine.compute(r, 32, mode_mask=1)[0] for r in rigs]
+    for _ in range(2):
+        batch = engine.compute_batch(rigs, 32, mode_mask=1)
+        for a, b in zip(single, batch):
+            assert (a == b[0]).all()
+
+
+def test_reference_class_mirror(engine):
+    import sister_b200
+    g = np.load(os.path.join(GOLDEN, "rig_64x48_d16.npz"))
+    views = make_rig(64, 48, 16, seed=int(g["seed"]), kind=str(g["kind"]), channels=3)
+    s = sister_b200.SisterMultiviewDisparities(*views, engine=engine)
+    mv, hz, vt = s.compute_disparities(16)
+    assert (mv == g["disp_mv"]).all() and (hz == g["disp_h"]).all() and (vt == g["disp_v"]).all()
+
+
+def test_config1_against_oracle(oracle_lib):
+    """BASELINE.json configs[0]: 640x480, D = 192, the multiview map, against the CPU oracle (a few seconds)."""
+    import sister_b200
+    views = make_rig(640, 480, 192, seed=1234, channels=1)
+    with sister_b200.Engine(640, 480, 192, n_slots=1) as eng:
+        outs, raw = eng.compute(views, 192, mode_mask=1, want_raw=True)
+    ref, ref_raw = oracle_lib.compute_disparities(views, 192, mode_mask=1, want_raw=True)
+    assert (raw[0] == ref_raw[0]).all(), f"{(raw[0] != ref_raw[0]).sum()} padded pixels differ"
+    assert (outs[0] == ref[0]).all()
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] shape (1280x960, D = 192): properties that need no CPU oracle."""
+    import sister_b200
+    D = 192
+    plane = make_rig(1280, 960, D, seed=7, kind="plane", noise=0, channels=1)
+    with sister_b200.Engine(1280, 960, D, n_slots=2) as eng:
+        a = eng.compute(plane, D, mode_mask=7)
+        b = eng.compute(plane, D, mode_mask=7)
+        for m in range(3):
+            assert (a[m] == b[m]).all(), "not deterministic"
+            d = a[m] // 255
+            assert (a[m] % 255 == 0).all()
+            inner = d[32:-32, 32:-32]
+            assert (inner == D // 3).mean() > 0.9, f"fronto-parallel plane not recovered in mode {m}"
+        batch = eng.compute_batch([plane, plane, plane], D, mode_mask=1)
+        for r in batch:
+            assert (r[0] == a[0]).all()
