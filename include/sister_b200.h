@@ -118,6 +118,10 @@ enum {
     SISTER_STAGE_COUNT
 };
 int sister_set_profiling(sister_ctx *ctx, int enabled);
+/* Device-time bracket over ALL slots' streams (CUDA events): begin waits for idle streams and fences them behind a
+ * start event; end joins every slot stream into an end event, synchronises and returns the elapsed milliseconds. */
+int sister_region_begin(sister_ctx *ctx);
+int sister_region_end(sister_ctx *ctx, float *elapsed_ms);
 int sister_get_stage_ms(sister_ctx *ctx, int slot, float *ms, int n);      /* summed over the modes run */
 int sister_get_stage_launches(sister_ctx *ctx, int slot, int *count, int n); /* kernel launches per stage, last submit */
 uint64_t sister_get_launch_count(sister_ctx *ctx);                          /* kernels launched since create */

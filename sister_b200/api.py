@@ -22,7 +22,7 @@ _i16p = C.POINTER(C.c_int16)
 ABI_SYMBOLS = (
     "sister_create", "sister_destroy", "sister_compute", "sister_compute_batch", "sister_submit", "sister_wait",
     "sister_submit_device", "sister_sync", "sister_dev_alloc", "sister_dev_free", "sister_dev_upload",
-    "sister_dev_download", "sister_set_profiling", "sister_get_stage_ms", "sister_get_stage_launches",
+    "sister_dev_download", "sister_set_profiling", "sister_region_begin", "sister_region_end", "sister_get_stage_ms", "sister_get_stage_launches",
     "sister_get_launch_count", "sister_debug_fetch", "sister_test_sgm", "sister_strerror", "sister_last_error",
     "sister_version",
 )
@@ -84,6 +84,10 @@ def load_library():
     L.sister_dev_download.restype = C.c_int
     L.sister_dev_download.argtypes = [vp, vp, vp, C.c_size_t]
     L.sister_set_profiling.argtypes = [vp, C.c_int]
+    L.sister_region_begin.restype = C.c_int
+    L.sister_region_begin.argtypes = [vp]
+    L.sister_region_end.restype = C.c_int
+    L.sister_region_end.argtypes = [vp, C.POINTER(C.c_float)]
     L.sister_get_stage_ms.restype = C.c_int
     L.sister_get_stage_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_int]
     L.sister_get_stage_launches.restype = C.c_int
@@ -225,6 +229,14 @@ class Engine:
     # -- measurement / taps
     def set_profiling(self, on: bool):
         self.lib.sister_set_profiling(self.ctx, int(on))
+
+    def region_begin(self):
+        self._chk(self.lib.sister_region_begin(self.ctx))
+
+    def region_end(self) -> float:
+        ms = C.c_float()
+        self._chk(self.lib.sister_region_end(self.ctx, C.byref(ms)))
+        return float(ms.value)
 
     def stage_ms(self, slot: int = 0):
         ms = (C.c_float * len(STAGE_NAMES))()

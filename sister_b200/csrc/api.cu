@@ -48,6 +48,8 @@ struct sister_ctx {
     size_t in_bytes_max = 0;
     std::vector<Slot> slots;
     bool profiling = false;
+    cudaEvent_t region_b = nullptr, region_e = nullptr;
+    std::vector<cudaEvent_t> region_join;
     LaunchCounter lc;
     std::string err;
 };
@@ -258,6 +260,8 @@ int sister_destroy(sister_ctx *ctx)
     if (!ctx) return SISTER_E_ARG;
     cudaSetDevice(ctx->device);
     for (auto &s : ctx->slots) free_slot(s);
+    if (ctx->region_b) { cudaEventDestroy(ctx->region_b); cudaEventDestroy(ctx->region_e); }
+    for (auto e : ctx->region_join) cudaEventDestroy(e);
     delete ctx;
     return SISTER_OK;
 }
@@ -408,6 +412,36 @@ int sister_set_profiling(sister_ctx *ctx, int enabled)
 {
     if (!ctx) return SISTER_E_ARG;
     ctx->profiling = enabled != 0;
+    return SISTER_OK;
+}
+
+int sister_region_begin(sister_ctx *ctx)
+{
+    if (!ctx) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    if (!ctx->region_b) {
+        SCK(cudaEventCreate(&ctx->region_b));
+        SCK(cudaEventCreate(&ctx->region_e));
+        ctx->region_join.resize(ctx->slots.size());
+        for (auto &e : ctx->region_join) SCK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    for (auto &s : ctx->slots) SCK(cudaStreamSynchronize(s.st));
+    SCK(cudaEventRecord(ctx->region_b, ctx->slots[0].st));
+    for (size_t k = 1; k < ctx->slots.size(); k++) SCK(cudaStreamWaitEvent(ctx->slots[k].st, ctx->region_b, 0));
+    return SISTER_OK;
+}
+
+int sister_region_end(sister_ctx *ctx, float *elapsed_ms)
+{
+    if (!ctx || !elapsed_ms || !ctx->region_b) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    for (size_t k = 1; k < ctx->slots.size(); k++) {
+        SCK(cudaEventRecord(ctx->region_join[k], ctx->slots[k].st));
+        SCK(cudaStreamWaitEvent(ctx->slots[0].st, ctx->region_join[k], 0));
+    }
+    SCK(cudaEventRecord(ctx->region_e, ctx->slots[0].st));
+    SCK(cudaEventSynchronize(ctx->region_e));
+    SCK(cudaEventElapsedTime(elapsed_ms, ctx->region_b, ctx->region_e));
     return SISTER_OK;
 }
 
