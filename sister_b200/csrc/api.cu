@@ -178,7 +178,6 @@ int slot_ok(sister_ctx *ctx, int slot)
 int finish_slot(sister_ctx *ctx, Slot &s)
 {
     SCK(cudaStreamSynchronize(s.st));
-    s.busy = false;
     if (*s.h_status != 0) {
         char buf[96];
         snprintf(buf, sizeof buf, "kernel invariant violated, status bits 0x%x", *s.h_status);
@@ -307,6 +306,7 @@ int sister_wait(sister_ctx *ctx, int slot, uint16_t *const out[3], int16_t *raw_
     if (!s.busy || !s.host_io) { ctx->err = "nothing submitted on this slot"; return SISTER_E_ARG; }
     SCK(cudaSetDevice(ctx->device));
     rc = finish_slot(ctx, s);
+    s.busy = false;
     if (rc) return rc;
     const size_t wh = (size_t)s.dims.W * s.dims.H;
     for (int m = 0; m < 3; m++)
@@ -358,10 +358,10 @@ int sister_submit_device(sister_ctx *ctx, int slot, const uint8_t *const views_d
     if (rc) return rc;
     Slot &s = ctx->slots[slot];
     SCK(cudaSetDevice(ctx->device));
+    if (s.busy && s.host_io) { ctx->err = "slot has an un-waited host submit"; return SISTER_E_BUSY; }
     rc = run_pipeline(ctx, s, views_dev, w * channels, channels, d, mode_mask, out_dev);
     if (rc) return rc;
-    s.busy = true;
-    s.host_io = false;
+    s.host_io = false; // device submits are ordered by the slot's stream; nothing to hand back on the host
     return SISTER_OK;
 }
 
