@@ -60,7 +60,8 @@ typedef struct sister_ctx sister_ctx;
 
 /* Create a context on CUDA device `device` able to process rigs up to max_w x max_h with up to
  * max_disp disparities, with n_slots rigs in flight (each slot owns a stream, pinned staging and all
- * scratch volumes: about (3 * cells + 48 * pixels) bytes, cells = (w+2D)(h+2D)D). */
+ * scratch volumes: about (9 * cells + 140 * pixels) bytes, cells = (w+2D)(h+2D)D: the uint8 fused volume
+ * and eight uint8 path volumes; 3.9 GB at 1280 x 960 x 192). */
 int sister_create(sister_ctx **ctx, int device, int max_w, int max_h, int max_disp, int n_slots);
 int sister_destroy(sister_ctx *ctx);
 
@@ -113,8 +114,9 @@ enum {
     SISTER_STAGE_MATCH,     /* raw Hamming cost + WTA left/right, 4 views  (census.cpp:54-146, postprocess.cpp:74-315) */
     SISTER_STAGE_MASK,      /* recursive median, LRC, confidence masks     (hpp:193-252)      */
     SISTER_STAGE_FUSE,      /* confidence-weighted fused volume            (hpp:255-277)      */
-    SISTER_STAGE_AGGREGATE, /* SGM, both passes                            (sgm.cpp:26-455)   */
-    SISTER_STAGE_SELECT,    /* final WTA + encode/crop                     (hpp:283,111-118)  */
+    SISTER_STAGE_AGGREGATE, /* SGM, both passes, + final WTA + encode/crop (sgm.cpp:26-455, hpp:283,111-118): the path
+                               kernel and the sum/WTA kernel                                   */
+    SISTER_STAGE_SELECT,    /* (folded into AGGREGATE: the final WTA reads the path volumes directly; always 0) */
     SISTER_STAGE_COUNT
 };
 int sister_set_profiling(sister_ctx *ctx, int enabled);
@@ -135,10 +137,13 @@ enum {
     SISTER_TAP_LR_FINAL,     /* 4 x px int16: left map after median + LRC (-10 = rejected), view frame    */
     SISTER_TAP_MASKS,        /* 4 x px uint8: confidence masks in the image frame                         */
     SISTER_TAP_FUSED,        /* cells uint8: fused volume of the LAST mode run, [row][col][d]             */
-    SISTER_TAP_SUM,          /* cells uint16: aggregated volume of the LAST mode run                      */
+    SISTER_TAP_SUM,          /* cells uint16: aggregated volume of the LAST mode run (needs sister_set_test_taps) */
     SISTER_TAP_RAW_DISP      /* 3 x px int16                                                              */
 };
 int sister_debug_fetch(sister_ctx *ctx, int slot, int what, void *host_dst, size_t bytes);
+/* The aggregated volume is not materialised by the product path (the final WTA consumes the path volumes directly);
+ * enabling the taps allocates it (2 * cells bytes per slot) and makes later submits write it for SISTER_TAP_SUM. */
+int sister_set_test_taps(sister_ctx *ctx, int enabled);
 
 /* Stage-level entry points for known-answer tests: run ONE stage on caller data (host pointers). */
 /* sgm(): fused volume uint8 [h][w][D] (values <= 252) -> aggregated uint16 [h][w][D] (sgm.cpp:457). */

@@ -25,7 +25,8 @@ struct Slot {
     unsigned long long *d_census = nullptr;
     int16_t *d_wtaL = nullptr, *d_wtaR = nullptr, *d_medL = nullptr, *d_medR = nullptr, *d_lr = nullptr;
     uint8_t *d_masks = nullptr, *d_fused = nullptr;
-    uint16_t *d_sum = nullptr;
+    uint8_t *d_paths = nullptr; // 8 one-byte path volumes (sgm.cu)
+    uint16_t *d_sum = nullptr;  // aggregated volume, allocated only while the test taps are enabled
     int16_t *d_raw = nullptr;
     uint16_t *d_out = nullptr, *h_out = nullptr;
     int *d_status = nullptr, *h_status = nullptr;
@@ -48,6 +49,7 @@ struct sister_ctx {
     size_t in_bytes_max = 0;
     std::vector<Slot> slots;
     bool profiling = false;
+    bool taps = false; // keep the aggregated volume for SISTER_TAP_SUM (tests only)
     cudaEvent_t region_b = nullptr, region_e = nullptr;
     std::vector<cudaEvent_t> region_join;
     LaunchCounter lc;
@@ -141,10 +143,8 @@ int run_pipeline(sister_ctx *ctx, Slot &s, const uint8_t *const in_views[5], int
         launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused, s.d_status, s.st, ctx->lc);
         end_stage(ctx, s);
         begin_stage(ctx, s, SISTER_STAGE_AGGREGATE);
-        launch_sgm(s.d_fused, d, s.d_sum, s.d_status, s.st, ctx->lc);
-        end_stage(ctx, s);
-        begin_stage(ctx, s, SISTER_STAGE_SELECT);
-        launch_select(s.d_sum, d, s.d_raw + (size_t)mode * d.px, out_dev ? out_dev[mode] : nullptr, s.st, ctx->lc);
+        launch_sgm(s.d_fused, d, s.d_paths, ctx->taps ? s.d_sum : nullptr, s.d_raw + (size_t)mode * d.px,
+                   out_dev ? out_dev[mode] : nullptr, s.d_status, s.st, ctx->lc);
         end_stage(ctx, s);
     }
     SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
@@ -160,7 +160,7 @@ void free_slot(Slot &s)
     if (s.st) cudaStreamSynchronize(s.st);
     cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_oriented); cudaFree(s.d_census);
     cudaFree(s.d_wtaL); cudaFree(s.d_wtaR); cudaFree(s.d_medL); cudaFree(s.d_medR); cudaFree(s.d_lr);
-    cudaFree(s.d_masks); cudaFree(s.d_fused); cudaFree(s.d_sum); cudaFree(s.d_raw); cudaFree(s.d_out);
+    cudaFree(s.d_masks); cudaFree(s.d_fused); cudaFree(s.d_paths); cudaFree(s.d_sum); cudaFree(s.d_raw); cudaFree(s.d_out);
     cudaFreeHost(s.h_out); cudaFree(s.d_status); cudaFreeHost(s.h_status);
     for (auto e : s.ev_b) cudaEventDestroy(e);
     for (auto e : s.ev_e) cudaEventDestroy(e);
@@ -241,7 +241,7 @@ int sister_create(sister_ctx **out, int device, int max_w, int max_h, int max_di
         A((void **)&s.d_oriented, 8 * px); A((void **)&s.d_census, 8 * px * 8);
         A((void **)&s.d_wtaL, 4 * px * 2); A((void **)&s.d_wtaR, 4 * px * 2);
         A((void **)&s.d_medL, 4 * px * 2); A((void **)&s.d_medR, 4 * px * 2); A((void **)&s.d_lr, 4 * px * 2);
-        A((void **)&s.d_masks, 4 * px); A((void **)&s.d_fused, cells); A((void **)&s.d_sum, cells * 2);
+        A((void **)&s.d_masks, 4 * px); A((void **)&s.d_fused, cells); A((void **)&s.d_paths, 8 * cells);
         A((void **)&s.d_raw, 3 * px * 2); A((void **)&s.d_out, 3 * wh * 2); H((void **)&s.h_out, 3 * wh * 2);
         A((void **)&s.d_status, sizeof(int)); H((void **)&s.h_status, sizeof(int));
         if (e != cudaSuccess) { rc = fail_cuda(nullptr, e, "alloc"); return bail(rc); }
@@ -408,6 +408,19 @@ int sister_dev_download(sister_ctx *ctx, void *host_dst, const void *dev_src, si
     return SISTER_OK;
 }
 
+int sister_set_test_taps(sister_ctx *ctx, int enabled)
+{
+    if (!ctx) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    for (auto &s : ctx->slots) {
+        SCK(cudaStreamSynchronize(s.st));
+        if (enabled && !s.d_sum) SCK(cudaMalloc((void **)&s.d_sum, (size_t)ctx->cells_max * 2));
+        if (!enabled && s.d_sum) { SCK(cudaFree(s.d_sum)); s.d_sum = nullptr; }
+    }
+    ctx->taps = enabled != 0;
+    return SISTER_OK;
+}
+
 int sister_set_profiling(sister_ctx *ctx, int enabled)
 {
     if (!ctx) return SISTER_E_ARG;
@@ -492,7 +505,9 @@ int sister_debug_fetch(sister_ctx *ctx, int slot, int what, void *host_dst, size
     case SISTER_TAP_LR_FINAL: src = s.d_lr; have = 4 * px * 2; break;
     case SISTER_TAP_MASKS: src = s.d_masks; have = 4 * px; break;
     case SISTER_TAP_FUSED: src = s.d_fused; have = cells; break;
-    case SISTER_TAP_SUM: src = s.d_sum; have = cells * 2; break;
+    case SISTER_TAP_SUM:
+        if (!ctx->taps || !s.d_sum) { ctx->err = "SISTER_TAP_SUM needs sister_set_test_taps(ctx, 1) before the submit"; return SISTER_E_ARG; }
+        src = s.d_sum; have = cells * 2; break;
     case SISTER_TAP_RAW_DISP: src = s.d_raw; have = 3 * px * 2; break;
     default: ctx->err = "unknown tap"; return SISTER_E_ARG;
     }
@@ -504,7 +519,7 @@ int sister_debug_fetch(sister_ctx *ctx, int slot, int what, void *host_dst, size
 int sister_test_sgm(sister_ctx *ctx, const uint8_t *fused, int w, int h, int disp_count, uint16_t *sum, int16_t *disp)
 {
     if (!ctx || !fused || !sum) return SISTER_E_ARG;
-    if (disp_count <= 0 || disp_count % 2 != 0 || disp_count > 512 || w < 2 || h < 2) { ctx->err = "bad sgm test shape"; return SISTER_E_SHAPE; }
+    if (disp_count <= 0 || disp_count % 8 != 0 || disp_count > 512 || w < 2 || h < 2) { ctx->err = "bad sgm test shape"; return SISTER_E_SHAPE; }
     Dims d;
     d.W = 0; d.H = 0; d.D = disp_count; d.Wp = w; d.Hp = h;
     d.px = (long long)w * h;
@@ -515,15 +530,15 @@ int sister_test_sgm(sister_ctx *ctx, const uint8_t *fused, int w, int h, int dis
     SCK(cudaSetDevice(ctx->device));
     SCK(cudaMemcpyAsync(s.d_fused, fused, (size_t)d.cells, cudaMemcpyHostToDevice, s.st));
     SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
+    if (!s.d_sum) SCK(cudaMalloc((void **)&s.d_sum, (size_t)ctx->cells_max * 2));
     ctx->lc.cur_stage = SISTER_STAGE_AGGREGATE;
-    launch_sgm(s.d_fused, d, s.d_sum, s.d_status, s.st, ctx->lc);
-    ctx->lc.cur_stage = SISTER_STAGE_SELECT;
-    launch_select(s.d_sum, d, s.d_raw, nullptr, s.st, ctx->lc);
+    launch_sgm(s.d_fused, d, s.d_paths, s.d_sum, s.d_raw, nullptr, s.d_status, s.st, ctx->lc);
     SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
     SCK(cudaGetLastError());
     SCK(cudaStreamSynchronize(s.st));
     SCK(cudaMemcpy(sum, s.d_sum, (size_t)d.cells * 2, cudaMemcpyDeviceToHost));
     if (disp) SCK(cudaMemcpy(disp, s.d_raw, (size_t)d.px * 2, cudaMemcpyDeviceToHost));
+    if (!ctx->taps) { SCK(cudaFree(s.d_sum)); s.d_sum = nullptr; }
     s.dims = d;
     return *s.h_status ? SISTER_E_INTERNAL : SISTER_OK;
 }

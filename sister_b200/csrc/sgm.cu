@@ -1,19 +1,32 @@
 // sister_b200 / sgm.cu -- semi-global aggregation and final selection (sm_100a).
 //
-// Restates accumulateCostsSSE (sgm.cpp:26-455; P1 = 7, P2 = 100, 2 passes x 4 paths) on the uint8 fused volume.
-// One warp works on one pixel: the D disparities are spread over the lanes, DPL = 2*NR consecutive disparities
-// per lane, two per 32-bit register as packed u16 (VIMNMX.U16x2 / VIADDMNMX.U16x2 / VIADD.16x2 on sm_100a).
+// Restates accumulateCostsSSE (sgm.cpp:26-455; P1 = 7, P2 = 100, 2 passes x 4 paths) on the uint8 fused volume C.
 //
-// State is kept NORMALISED: A(d) = L(d) - min_d L. With it the reference's update
-//     L'(d) = C(d) (+) ( min(L(d), L(d-1) (+) P1, L(d+1) (+) P1, P2 (+) m) (-) m )           sgm.cpp:282-297
-// becomes L'(d) = C(d) + min(A(d), A(d-1) + P1, A(d+1) + P1, P2), which needs no saturation because C <= 252
-// (match.cu) gives L' <= 352 and the 8-path sum <= 2816. The reference's sentinels map as follows:
-//     L(-1) = L(D) = 65535 (sgm.cpp:84-87)                 -> kInf2 in the neighbour slots (never the minimum)
-//     off-image predecessor column: L = 65535, m = 0       -> A = kInf2 everywhere  => L' = C + P2  (sgm.cpp:57-81)
-//     r0 at the start of a row: L = 0, m = 0               -> A = 0 everywhere      => L' = C       (sgm.cpp:215-216)
-//     first line of a pass: L1 = L2 = L3 = C, m = min C    -> A = C - min C, no contribution to the sum (sgm.cpp:103-138)
-//     first line, r0: int32 arithmetic + 8-bit truncation  -> k_sgm_first_line (sgm.cpp:141-190, types.h:28)
-// The "cost == 255 -> 0" substitution of sgm.cpp:109,123,146 can never fire on C <= 252.
+// Decomposition (proven equal to the reference recurrence on the CPU by tests/sgm_spec.py):
+//   * Each of the 8 paths is a set of INDEPENDENT chains (rows for r0, columns for r2, wrapped diagonals for r1/r3).
+//     One warp follows one chain; the D disparities are spread over the lanes, 2*NR consecutive disparities per
+//     lane, two per 32-bit register as packed 16-bit lanes (VIADDMNMX.S16x2 / VIMNMX.S16x2 on sm_100a).
+//   * The state a chain carries is normalised and clamped:  a(d) = min(L(d) - min_d L, P2).  With it the reference update
+//         L'(d) = C(d) (+) ( min(L(d), L(d-1) (+) P1, L(d+1) (+) P1, P2 (+) m) (-) m )                 sgm.cpp:282-297
+//     becomes  Q(d) = min(a(d), a(d-1) + P1, a(d+1) + P1),  L'(d) = C(d) + Q(d),  with no saturation anywhere because
+//     C <= 252 (match.cu) bounds L' by 352 and the 8-path sum by 2816. The reference's sentinels map as follows:
+//         L(-1) = L(D) = 65535 (sgm.cpp:84-87)                 -> kInf2 in the neighbour slots (never the minimum)
+//         off-image predecessor column: L = 65535, m = 0       -> a = P2 everywhere  => Q = P2   (sgm.cpp:57-81)
+//         r0 at the start of a row: L = 0, m = 0               -> a = 0 everywhere   => Q = 0    (sgm.cpp:215-216)
+//         first line of a pass: L1 = L2 = L3 = C, m = min C    -> a = min(C - min C, P2), nothing added to the sum
+//         first line, r0: int32 arithmetic + 8-bit truncation  -> first_line_step (sgm.cpp:141-190, types.h:28)
+//     The "cost == 255 -> 0" substitution of sgm.cpp:109,123,146 can never fire on C <= 252.
+//   * A chain does not touch the sum volume. It emits the penalty term Q(d) = L'(d) - C(d) in [0, P2] as ONE BYTE per
+//     cell into the path's own volume (a diagonal chain that leaves the frame re-enters at the opposite border with
+//     a = P2, so every column/diagonal chain has exactly Hp steps and every cell of a path volume is written once).
+//   * k_sgm_final adds up  S = nC * C + sum of the 8 path bytes  (nC = 8, or 4 on the first line of either pass where
+//     r1..r3 contribute nothing and r0's byte is the whole truncated value) and does the final WTA (hpp:283) and the
+//     output encoding (hpp:111-118) in the same sweep; S itself is only written when a test asks for it.
+//
+// Traffic per padded cell: 8 x (1 B read C + 1 B write Q) + (1 + 8) B read = 25 B, no read-modify-write, against
+// 40 B for the path-by-path accumulation into a uint16 sum volume this replaces. The fused-cost rows a chain will
+// need are known in advance, so each warp keeps kRing steps of C in flight with cp.async (LDGSTS) into a private
+// shared-memory ring; nothing in a chain step waits on DRAM.
 #include "kernels.cuh"
 
 namespace sister {
@@ -21,17 +34,17 @@ namespace sister {
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint32_t kP1x2 = (uint32_t)kP1 * 0x10001u;
 constexpr uint32_t kP2x2 = (uint32_t)kP2 * 0x10001u;
+constexpr int kRing = 12;         // steps of fused cost in flight per warp
+constexpr int kChainWarps = 8;    // warps (= chains) per block
 
-struct PassGeom {
-    int i1, di, j1, dj, jl; // first line, row step, first column, column step, last column in scan order
-};
-__host__ __device__ inline PassGeom pass_geom(const Dims &d, int pass)
+// ---------------------------------------------------------------------------------------------- small helpers
+
+__device__ __forceinline__ void cp_async8(unsigned smem_dst, const void *gmem_src)
 {
-    PassGeom g;
-    if (pass == 0) { g.i1 = 0; g.di = 1; g.j1 = 0; g.dj = 1; g.jl = d.Wp - 1; }
-    else { g.i1 = d.Hp - 1; g.di = -1; g.j1 = d.Wp - 1; g.dj = -1; g.jl = 0; }
-    return g;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // number of valid packed registers of this lane (disparities lane*2NR + 2k, +1 are valid for k < nvalid)
 template <int NR> __device__ __forceinline__ int lane_nvalid(int D, int lane)
@@ -40,214 +53,312 @@ template <int NR> __device__ __forceinline__ int lane_nvalid(int D, int lane)
     return n < 0 ? 0 : (n > NR ? NR : n);
 }
 
-template <int NR> __device__ __forceinline__ void load_cost(const uint8_t *__restrict__ pix, int lane, int nvalid, uint32_t (&c)[NR])
-{
-    const uint16_t *p = reinterpret_cast<const uint16_t *>(pix) + lane * NR;
-#pragma unroll
-    for (int k = 0; k < NR; k++) c[k] = (k < nvalid) ? __byte_perm((uint32_t)p[k], 0u, 0x4140) : 0u;
-}
-
-__device__ __forceinline__ unsigned warp_min_u16x2(uint32_t m2)
+__device__ __forceinline__ unsigned warp_min_s16x2(uint32_t m2)
 {
     unsigned m = min(m2 & 0xFFFFu, m2 >> 16);
     return __reduce_min_sync(kFull, m);
 }
 
-// One SGM step for one path at one pixel. A: normalised state of the predecessor (pad registers = kInf2).
-// Writes L (pad registers = kInf2) and returns min_d L.
-template <int NR>
-__device__ __forceinline__ unsigned path_step(const uint32_t (&A)[NR], const uint32_t (&c)[NR], int lane, int nvalid, uint32_t (&L)[NR])
+// Neighbour registers of a packed state vector: E[k] = (d-1 of the low half, low half), E[k+1] = (high half, d+1 of
+// the high half). The two values that live in the adjacent lanes come by shuffle; the outermost ones are kInf2.
+template <int NR> __device__ __forceinline__ void neighbours(const uint32_t (&a)[NR], int lane, uint32_t (&E)[NR + 1])
 {
-    uint32_t up = __shfl_up_sync(kFull, A[NR - 1], 1);
-    uint32_t dn = __shfl_down_sync(kFull, A[0], 1);
+    uint32_t up = __shfl_up_sync(kFull, a[NR - 1], 1);
+    uint32_t dn = __shfl_down_sync(kFull, a[0], 1);
     if (lane == 0) up = kInf2;
     if (lane == 31) dn = kInf2;
-    uint32_t E[NR + 1]; // E[k] = (d-1 of the low half, low half) ; E[k+1] = (high half, d+1 of the high half)
-    E[0] = __byte_perm(up, A[0], 0x5432);
+    E[0] = __byte_perm(up, a[0], 0x5432);
 #pragma unroll
-    for (int k = 1; k < NR; k++) E[k] = __byte_perm(A[k - 1], A[k], 0x5432);
-    E[NR] = __byte_perm(A[NR - 1], dn, 0x5432);
+    for (int k = 1; k < NR; k++) E[k] = __byte_perm(a[k - 1], a[k], 0x5432);
+    E[NR] = __byte_perm(a[NR - 1], dn, 0x5432);
+}
+
+// One SGM step of one chain: a = clamped normalised state of the predecessor (pad registers = kInf2).
+// Writes q = L' - C (in [0, P2]) and the new state.
+template <int NR, bool FULL>
+__device__ __forceinline__ void chain_step(uint32_t (&a)[NR], const uint32_t (&c)[NR], int lane, int nvalid, uint32_t (&q)[NR])
+{
+    uint32_t E[NR + 1], L[NR];
+    neighbours<NR>(a, lane, E);
     uint32_t m2 = kInf2;
 #pragma unroll
     for (int k = 0; k < NR; k++) {
-        uint32_t x = __viaddmin_u16x2(E[k], kP1x2, A[k]);
-        uint32_t y = __viaddmin_u16x2(E[k + 1], kP1x2, kP2x2);
-        uint32_t l = __vminu2(x, y) + c[k];
-        L[k] = (k < nvalid) ? l : kInf2;
-        m2 = __vminu2(m2, L[k]);
+        const uint32_t x = __viaddmin_s16x2(E[k], kP1x2, a[k]);
+        q[k] = __viaddmin_s16x2(E[k + 1], kP1x2, x);
+        L[k] = q[k] + c[k];
+        if (FULL || k < nvalid) m2 = __vmins2(m2, L[k]);
     }
-    return warp_min_u16x2(m2);
-}
-
-template <int NR> __device__ __forceinline__ void normalise(const uint32_t (&L)[NR], unsigned m, int nvalid, uint32_t (&A)[NR])
-{
-    const uint32_t mm = m * 0x10001u;
+    const unsigned m = warp_min_s16x2(m2);
+    const uint32_t neg = ((0u - m) & 0xFFFFu) * 0x10001u; // (-m, -m) as packed s16
 #pragma unroll
-    for (int k = 0; k < NR; k++) A[k] = (k < nvalid) ? (L[k] - mm) : kInf2;
-}
-
-template <int NR> __device__ __forceinline__ void sum_add(uint16_t *__restrict__ spix, int lane, int nvalid, const uint32_t (&L)[NR])
-{
-    uint32_t *p = reinterpret_cast<uint32_t *>(spix) + lane * NR;
-#pragma unroll
-    for (int k = 0; k < NR; k++)
-        if (k < nvalid) p[k] += L[k];
-}
-
-// ------------------------------------------------------------------------------------ first line, path r0
-// One warp per launch: the horizontal path on the first line of a pass (sgm.cpp:141-190): plain int arithmetic,
-// then saturate_cast<uint16>(uint8) truncation (types.h:28) -- the state carried along the line is the truncated
-// value, not normalised.
-template <int NR> __global__ void __launch_bounds__(32) k_sgm_first_line(const uint8_t *__restrict__ fused, Dims d, int pass, uint16_t *__restrict__ sum)
-{
-    const int lane = threadIdx.x;
-    const int nvalid = lane_nvalid<NR>(d.D, lane);
-    const PassGeom g = pass_geom(d, pass);
-    uint32_t Lq[NR], c[NR];
-    unsigned m = 0;
-    for (int j = g.j1, n = 0; n < d.Wp; j += g.dj, n++) {
-        const size_t pix = (size_t)g.i1 * d.Wp + j;
-        load_cost<NR>(fused + pix * d.D, lane, nvalid, c);
-        uint32_t nw[NR];
-        if (n == 0) {
-#pragma unroll
-            for (int k = 0; k < NR; k++) nw[k] = (k < nvalid) ? c[k] : kInf2;
-        } else {
-            uint32_t up = __shfl_up_sync(kFull, Lq[NR - 1], 1);
-            uint32_t dn = __shfl_down_sync(kFull, Lq[0], 1);
-            if (lane == 0) up = kInf2;
-            if (lane == 31) dn = kInf2;
-            uint32_t E[NR + 1];
-            E[0] = __byte_perm(up, Lq[0], 0x5432);
-#pragma unroll
-            for (int k = 1; k < NR; k++) E[k] = __byte_perm(Lq[k - 1], Lq[k], 0x5432);
-            E[NR] = __byte_perm(Lq[NR - 1], dn, 0x5432);
-            const uint32_t mm = m * 0x10001u, p2 = mm + kP2x2;
-#pragma unroll
-            for (int k = 0; k < NR; k++) {
-                uint32_t x = __viaddmin_u16x2(E[k], kP1x2, Lq[k]);
-                uint32_t y = __viaddmin_u16x2(E[k + 1], kP1x2, p2);
-                uint32_t t = __vminu2(x, y) - mm;
-                nw[k] = (k < nvalid) ? ((c[k] + t) & 0x00FF00FFu) : kInf2;
-            }
-        }
-        uint32_t m2 = kInf2;
-#pragma unroll
-        for (int k = 0; k < NR; k++) { Lq[k] = nw[k]; m2 = __vminu2(m2, nw[k]); }
-        m = warp_min_u16x2(m2);
-        sum_add<NR>(sum + pix * d.D, lane, nvalid, nw);
+    for (int k = 0; k < NR; k++) {
+        const uint32_t n = __viaddmin_s16x2(L[k], neg, kP2x2); // min(L - m, P2)
+        a[k] = (FULL || k < nvalid) ? n : kInf2;
     }
 }
 
-// ------------------------------------------------------------------------------------ path chains
-// One warp follows one path chain of one direction through the frame and adds its L into the sum volume.
-// (Correctness-first decomposition: every path is an independent kernel; paths commute because nothing saturates.)
-//   path 0: r0, predecessor (i, j - dj)       chains = rows other than the first line, start state A = 0
-//   path 1: r1, predecessor (i - di, j - dj)  chains start on the first line (state from C) or at column j1 (A = inf)
-//   path 2: r2, predecessor (i - di, j)       chains start on the first line
-//   path 3: r3, predecessor (i - di, j + dj)  chains start on the first line or at the last column (A = inf)
-template <int NR>
-__global__ void __launch_bounds__(256) k_sgm_chains(const uint8_t *__restrict__ fused, Dims d, int pass, int path, uint16_t *__restrict__ sum)
+// The first cell of a column / diagonal chain lies on the first line of the pass: L = C (sgm.cpp:103-138).
+template <int NR, bool FULL>
+__device__ __forceinline__ void chain_first_cell(uint32_t (&a)[NR], const uint32_t (&c)[NR], int nvalid, uint32_t (&q)[NR])
 {
-    const int lane = threadIdx.x & 31;
-    const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const PassGeom g = pass_geom(d, pass);
-    const int row_off = (pass == 0) ? 1 : 0; // rows other than the first line: row_off .. row_off + Hp - 2
-    int i, j, si, sj, init; // init 0: A = 0; 1: first-line cell; 2: A = inf
-    if (path == 0) {
-        if (chain >= d.Hp - 1) return;
-        i = chain + row_off; j = g.j1; si = 0; sj = g.dj; init = 0;
-    } else if (path == 2) {
-        if (chain >= d.Wp) return;
-        i = g.i1; j = chain; si = g.di; sj = 0; init = 1;
+    uint32_t m2 = kInf2;
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+        q[k] = 0u;
+        if (FULL || k < nvalid) m2 = __vmins2(m2, c[k]);
+    }
+    const unsigned m = warp_min_s16x2(m2);
+    const uint32_t neg = ((0u - m) & 0xFFFFu) * 0x10001u;
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+        const uint32_t n = __viaddmin_s16x2(c[k], neg, kP2x2);
+        a[k] = (FULL || k < nvalid) ? n : kInf2;
+    }
+}
+
+// The horizontal path on the first line of a pass (sgm.cpp:141-190): plain int arithmetic on the un-normalised
+// values, then saturate_cast<uint16>(uint8) truncation (types.h:28). The state carried along the line is the truncated
+// value Lq and its minimum m; the byte written to the path volume is the truncated value itself.
+template <int NR, bool FULL>
+__device__ __forceinline__ void first_line_step(uint32_t (&Lq)[NR], unsigned &m, const uint32_t (&c)[NR], int lane, int nvalid,
+                                                bool first_column, uint32_t (&q)[NR])
+{
+    if (first_column) {
+#pragma unroll
+        for (int k = 0; k < NR; k++) q[k] = c[k];
     } else {
-        if (chain >= d.Wp + d.Hp - 1) return;
-        si = g.di; sj = (path == 1) ? g.dj : -g.dj;
-        if (chain < d.Wp) { i = g.i1; j = chain; init = 1; }
-        else { i = chain - d.Wp + row_off; j = (path == 1) ? g.j1 : g.jl; init = 2; }
-    }
-    const int nvalid = lane_nvalid<NR>(d.D, lane);
-    uint32_t A[NR], c[NR], L[NR];
-#pragma unroll
-    for (int k = 0; k < NR; k++) A[k] = (init == 0 && k < nvalid) ? 0u : kInf2;
-    bool first_line_cell = (init == 1);
-    while (i >= 0 && i < d.Hp && j >= 0 && j < d.Wp) {
-        const size_t pix = (size_t)i * d.Wp + j;
-        load_cost<NR>(fused + pix * d.D, lane, nvalid, c);
-        if (first_line_cell) {
-            uint32_t m2 = kInf2;
-#pragma unroll
-            for (int k = 0; k < NR; k++) { L[k] = (k < nvalid) ? c[k] : kInf2; m2 = __vminu2(m2, L[k]); }
-            normalise<NR>(L, warp_min_u16x2(m2), nvalid, A);
-            first_line_cell = false;
-        } else {
-            unsigned m = path_step<NR>(A, c, lane, nvalid, L);
-            sum_add<NR>(sum + pix * d.D, lane, nvalid, L);
-            normalise<NR>(L, m, nvalid, A);
-        }
-        i += si; j += sj;
-    }
-}
-
-template <int NR> static void launch_sgm_nr(const uint8_t *fused, const Dims &d, uint16_t *sum, cudaStream_t st, LaunchCounter &lc)
-{
-    cudaMemsetAsync(sum, 0, (size_t)d.cells * sizeof(uint16_t), st);
-    const int wpb = 8;
-    for (int pass = 0; pass < 2; pass++) {
-        k_sgm_first_line<NR><<<1, 32, 0, st>>>(fused, d, pass, sum);
-        lc.add();
-        for (int path = 0; path < 4; path++) {
-            int chains = path == 0 ? d.Hp - 1 : path == 2 ? d.Wp : d.Wp + d.Hp - 1;
-            k_sgm_chains<NR><<<(chains + wpb - 1) / wpb, wpb * 32, 0, st>>>(fused, d, pass, path, sum);
-            lc.add();
-        }
-    }
-}
-
-// disparities per lane = 2 * NR, chosen so that D fits in 32 lanes
-static int pick_nr(int D) { return (D + 63) / 64; }
-
-void launch_sgm(const uint8_t *fused, const Dims &d, uint16_t *sum, int *status, cudaStream_t st, LaunchCounter &lc)
-{
-    (void)status;
-    switch (pick_nr(d.D)) {
-    case 1: launch_sgm_nr<1>(fused, d, sum, st, lc); break;
-    case 2: launch_sgm_nr<2>(fused, d, sum, st, lc); break;
-    case 3: launch_sgm_nr<3>(fused, d, sum, st, lc); break;
-    case 4: launch_sgm_nr<4>(fused, d, sum, st, lc); break;
-    case 5: launch_sgm_nr<5>(fused, d, sum, st, lc); break;
-    case 6: launch_sgm_nr<6>(fused, d, sum, st, lc); break;
-    case 7: launch_sgm_nr<7>(fused, d, sum, st, lc); break;
-    default: launch_sgm_nr<8>(fused, d, sum, st, lc); break;
-    }
-}
-
-// ------------------------------------------------------------------------------------ final WTA + encode
-// WTALeft_SSE with uniqueness 1 (hpp:283): first-index argmin over d <= min(j, D-1); then convertTo(CV_16UC1),
-// crop Rect(D, D, W, H) and * 255 with saturation (hpp:111-118). One warp per pixel.
-template <int NR>
-__global__ void __launch_bounds__(256) k_select(const uint16_t *__restrict__ sum, Dims d, int16_t *__restrict__ raw_disp, uint16_t *__restrict__ out)
-{
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
-    const int nvalid = lane_nvalid<NR>(d.D, lane);
-    for (long long pix = warp0; pix < d.px; pix += nw) {
-        const int i = (int)(pix / d.Wp), j = (int)(pix % d.Wp);
-        const int dmax = min(j, d.D - 1);
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(sum + pix * d.D) + lane * NR;
-        unsigned best = 0xFFFFFFFFu;
+        uint32_t E[NR + 1];
+        neighbours<NR>(Lq, lane, E);
+        const uint32_t mm = m * 0x10001u, p2 = mm + kP2x2;
 #pragma unroll
         for (int k = 0; k < NR; k++) {
-            if (k < nvalid) {
-                const uint32_t s2 = p[k];
-                const int d0 = lane * 2 * NR + 2 * k;
-                if (d0 <= dmax) best = min(best, ((s2 & 0xFFFFu) << 16) | (unsigned)d0);
-                if (d0 + 1 <= dmax) best = min(best, (s2 & 0xFFFF0000u) | (unsigned)(d0 + 1));
+            const uint32_t x = __viaddmin_s16x2(E[k], kP1x2, Lq[k]);
+            const uint32_t y = __viaddmin_s16x2(E[k + 1], kP1x2, p2);
+            q[k] = (c[k] + (__vmins2(x, y) - mm)) & 0x00FF00FFu;
+        }
+    }
+    uint32_t m2 = kInf2;
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+        Lq[k] = (FULL || k < nvalid) ? q[k] : kInf2;
+        m2 = __vmins2(m2, Lq[k]);
+    }
+    m = warp_min_s16x2(m2);
+}
+
+// ---------------------------------------------------------------------------------------------- chain geometry
+
+struct Chain {
+    int i, j;       // first cell
+    int si, sj;     // step
+    int enter;      // column a diagonal chain re-enters at after leaving the frame
+    int nsteps;
+    int vol;        // path volume index: 4 * pass + path
+    int kind;       // 0: r0 on an ordinary row (a = 0), 1: r0 on the first line, 2: column / diagonal chain
+};
+
+// Chain numbering: [2 first-line r0 chains][2 * (Hp-1) row chains][2 * 3 * Wp column and diagonal chains]
+__host__ __device__ inline long long chain_count(const Dims &d) { return 2 + 2LL * (d.Hp - 1) + 6LL * d.Wp; }
+
+__device__ __forceinline__ bool chain_decode(const Dims &d, long long g, Chain &ch)
+{
+    if (g >= chain_count(d)) return false;
+    if (g < 2) {
+        const int p = (int)g;
+        ch.i = p ? d.Hp - 1 : 0; ch.j = p ? d.Wp - 1 : 0; ch.si = 0; ch.sj = p ? -1 : 1; ch.enter = 0;
+        ch.nsteps = d.Wp; ch.vol = 4 * p; ch.kind = 1;
+        return true;
+    }
+    g -= 2;
+    if (g < 2LL * (d.Hp - 1)) {
+        const int p = (int)(g / (d.Hp - 1)), r = (int)(g % (d.Hp - 1));
+        ch.i = p ? r : r + 1; ch.j = p ? d.Wp - 1 : 0; ch.si = 0; ch.sj = p ? -1 : 1; ch.enter = 0;
+        ch.nsteps = d.Wp; ch.vol = 4 * p; ch.kind = 0;
+        return true;
+    }
+    g -= 2LL * (d.Hp - 1);
+    const int p = (int)(g / (3LL * d.Wp));
+    const int rem = (int)(g % (3LL * d.Wp)), col = rem / 3, type = rem % 3; // type 0: r1, 1: r2, 2: r3
+    const int dj = p ? -1 : 1, j1 = p ? d.Wp - 1 : 0, jl = p ? 0 : d.Wp - 1;
+    ch.i = p ? d.Hp - 1 : 0; ch.j = col; ch.si = dj;
+    ch.sj = type == 0 ? dj : type == 1 ? 0 : -dj;
+    ch.enter = type == 0 ? j1 : jl;
+    ch.nsteps = d.Hp; ch.vol = 4 * p + 1 + type; ch.kind = 2;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------- the path kernel
+
+// grid ceil(chain_count / kChainWarps), block kChainWarps * 32, dynamic smem kChainWarps * kRing * 64 * NR bytes
+template <int NR, bool FULL>
+__global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, uint8_t *__restrict__ qvol)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kSlotBytes = 64 * NR;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Chain ch;
+    if (!chain_decode(d, (long long)blockIdx.x * kChainWarps + warp, ch)) return;
+    const int D = d.D, Wp = d.Wp;
+    const int nvalid = FULL ? NR : lane_nvalid<NR>(D, lane);
+
+    // Cursors advance by a constant byte stride; a diagonal chain that steps over a side border re-enters at the
+    // opposite one (same row), which is a fixed correction of one row of cells.
+    const long long stride = ((long long)ch.si * Wp + ch.sj) * D;
+    const long long wrapfix = -(long long)ch.sj * Wp * D;
+    const size_t first_cell = ((size_t)ch.i * Wp + ch.j) * D;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)warp * kRing * kSlotBytes);
+    constexpr unsigned kRingBytes = kRing * kSlotBytes;
+
+    // prefetch cursor: lane l fetches bytes [8l, 8l+8) and [8l+256, 8l+264) of the cell's D cost bytes
+    const uint8_t *psrc = fused + first_cell + lane * 8;
+    int pj = ch.j;
+    const bool ld0 = lane * 8 < D, ld1 = lane * 8 + 256 < D;
+    auto issue = [&](unsigned slot_off) {
+        if (ld0) cp_async8(ring_s + slot_off + lane * 8, psrc);
+        if (NR > 4 && ld1) cp_async8(ring_s + slot_off + lane * 8 + 256, psrc + 256);
+    };
+    auto padvance = [&]() {
+        psrc += stride; pj += ch.sj;
+        if ((unsigned)pj >= (unsigned)Wp) { pj = ch.enter; psrc += wrapfix; }
+    };
+#pragma unroll 1
+    for (int t = 0; t < kRing - 1; t++) {
+        if (t < ch.nsteps) issue(t * kSlotBytes);
+        cp_async_commit();
+        padvance();
+    }
+
+    uint32_t a[NR], c[NR], q[NR];
+#pragma unroll
+    for (int k = 0; k < NR; k++) a[k] = (k < nvalid) ? 0u : kInf2; // r0 at the start of a row (sgm.cpp:215-216)
+    unsigned m_first = 0;
+    uint8_t *qdst = qvol + (size_t)ch.vol * (size_t)d.cells + first_cell + lane * 2 * NR;
+    int j = ch.j;
+    unsigned rd_off = 0, wr_off = (kRing - 1) * kSlotBytes;
+    int to_issue = ch.nsteps - (kRing - 1);
+    bool reset = false;
+#pragma unroll 1
+    for (int s = 0; s < ch.nsteps; s++) {
+        cp_async_wait<kRing - 2>();
+        __syncwarp();
+        {
+            const unsigned src = ring_s + rd_off + lane * 2 * NR;
+#pragma unroll
+            for (int k = 0; k < NR; k++) {
+                unsigned short v;
+                asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(src + 2 * k) : "memory");
+                c[k] = __byte_perm((uint32_t)v, 0u, 0x4140);
             }
         }
-        best = __reduce_min_sync(kFull, best);
-        if (lane == 0) {
+        if (to_issue > 0) issue(wr_off);
+        to_issue--;
+        cp_async_commit();
+        padvance();
+
+        if (ch.kind == 1) {
+            first_line_step<NR, FULL>(a, m_first, c, lane, nvalid, s == 0, q);
+        } else if (ch.kind == 2 && s == 0) {
+            chain_first_cell<NR, FULL>(a, c, nvalid, q);
+        } else {
+            if (reset) {
+#pragma unroll
+                for (int k = 0; k < NR; k++) a[k] = (FULL || k < nvalid) ? kP2x2 : kInf2; // sgm.cpp:57-81
+            }
+            chain_step<NR, FULL>(a, c, lane, nvalid, q);
+        }
+
+        // one byte per cell: q <= 255 in both halves
+        uint8_t *dst = qdst;
+        if constexpr (NR % 2 == 0) {
+            // lane * 2NR is a multiple of 4 and pix * D a multiple of 8: 32-bit stores are always aligned
+            if (FULL || nvalid == NR) {
+                uint32_t w[NR / 2];
+#pragma unroll
+                for (int k = 0; k < NR / 2; k++) w[k] = __byte_perm(q[2 * k], q[2 * k + 1], 0x6420);
+                if constexpr (FULL && NR == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+                else if constexpr (FULL && NR == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                else {
+#pragma unroll
+                    for (int k = 0; k < NR / 2; k++) reinterpret_cast<uint32_t *>(dst)[k] = w[k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NR; k++)
+                    if (k < nvalid) reinterpret_cast<uint16_t *>(dst)[k] = (uint16_t)__byte_perm(q[k], 0u, 0x4420);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NR; k++)
+                if (FULL || k < nvalid) reinterpret_cast<uint16_t *>(dst)[k] = (uint16_t)__byte_perm(q[k], 0u, 0x4420);
+        }
+
+        qdst += stride; j += ch.sj;
+        reset = (unsigned)j >= (unsigned)Wp;
+        if (reset) { j = ch.enter; qdst += wrapfix; }
+        rd_off = (rd_off + kSlotBytes == kRingBytes) ? 0u : rd_off + kSlotBytes;
+        wr_off = (wr_off + kSlotBytes == kRingBytes) ? 0u : wr_off + kSlotBytes;
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------- final sum + WTA + encode
+
+__device__ __forceinline__ uint2 ldg8(const uint8_t *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
+
+// S = nC * C + sum_v Q_v; WTALeft_SSE with uniqueness 1 (hpp:283): first-index argmin over d <= min(j, D-1); then
+// convertTo(CV_16UC1), crop Rect(D, D, W, H) and * 255 with saturation (hpp:111-118).
+// Eight lanes per pixel, each lane owns 8-byte chunks sub, sub + 8, ... of the pixel's D bytes in all nine volumes.
+// grid-stride over groups of 4 pixels per warp.
+__global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ fused, const uint8_t *__restrict__ qvol, Dims d,
+                                                   uint16_t *__restrict__ sum, int16_t *__restrict__ raw_disp, uint16_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int D = d.D, nchunk = D >> 3;
+    const size_t cells = (size_t)d.cells;
+    for (long long base = warp0 * 4; base < d.px; base += nwarps * 4) {
+        const long long pix = base + grp;
+        const bool live = pix < d.px;
+        const int i = live ? (int)(pix / d.Wp) : 0, j = live ? (int)(pix % d.Wp) : 0;
+        const int dmax = min(j, D - 1);
+        const int sh = (i == 0 || i == d.Hp - 1) ? 2 : 3; // nC = 4 on the first line of either pass, else 8
+        unsigned best = 0xFFFFFFFFu;
+        if (live) {
+            const size_t off0 = (size_t)pix * D;
+            for (int chunk = sub; chunk < nchunk; chunk += 8) {
+                const int d0 = chunk * 8;
+                const size_t off = off0 + d0;
+                const uint2 cc = ldg8(fused + off);
+                uint2 qq[8];
+#pragma unroll
+                for (int v = 0; v < 8; v++) qq[v] = ldg8(qvol + (size_t)v * cells + off);
+                // byte-wise pair sums stay below 256 except on first lines (r0's byte may be up to 255 there, its
+                // partner r1 writes 0), so a plain 32-bit add is a 4-lane byte add
+                uint32_t w[2][4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { w[0][k] = qq[2 * k].x + qq[2 * k + 1].x; w[1][k] = qq[2 * k].y + qq[2 * k + 1].y; }
+                uint32_t S[4]; // 8 cells as packed u16: S[0] = d0, d0+1; S[1] = d0+2, d0+3; ...
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t cw = h ? cc.y : cc.x;
+                    uint32_t lo = __byte_perm(cw, 0u, 0x4140) << sh, hi = __byte_perm(cw, 0u, 0x4342) << sh;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { lo += __byte_perm(w[h][k], 0u, 0x4140); hi += __byte_perm(w[h][k], 0u, 0x4342); }
+                    S[2 * h] = lo; S[2 * h + 1] = hi;
+                }
+                if (sum) *reinterpret_cast<uint4 *>(sum + off) = make_uint4(S[0], S[1], S[2], S[3]);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int da = d0 + 2 * k;
+                    if (da <= dmax) best = min(best, ((S[k] & 0xFFFFu) << 16) | (unsigned)da);
+                    if (da + 1 <= dmax) best = min(best, (S[k] & 0xFFFF0000u) | (unsigned)(da + 1));
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) best = min(best, __shfl_xor_sync(kFull, best, o));
+        if (live && sub == 0) {
             const int disp = (int)(best & 0xFFFFu);
             if (raw_disp) raw_disp[pix] = (int16_t)disp;
             const int oi = i - d.D, oj = j - d.D;
@@ -256,16 +367,46 @@ __global__ void __launch_bounds__(256) k_select(const uint16_t *__restrict__ sum
     }
 }
 
-void launch_select(const uint16_t *sum, const Dims &d, int16_t *raw_disp, uint16_t *out, cudaStream_t st, LaunchCounter &lc)
+// ---------------------------------------------------------------------------------------------- launch
+
+template <int NR, bool FULL>
+static void launch_paths(const uint8_t *fused, const Dims &d, uint8_t *qvol, cudaStream_t st)
 {
-    const int blocks = 148 * 8;
-#define SISTER_SELECT_CASE(N) case N: k_select<N><<<blocks, 256, 0, st>>>(sum, d, raw_disp, out); break;
-    switch (pick_nr(d.D)) {
-        SISTER_SELECT_CASE(1) SISTER_SELECT_CASE(2) SISTER_SELECT_CASE(3) SISTER_SELECT_CASE(4)
-        SISTER_SELECT_CASE(5) SISTER_SELECT_CASE(6) SISTER_SELECT_CASE(7)
-    default: k_select<8><<<blocks, 256, 0, st>>>(sum, d, raw_disp, out); break;
+    const size_t smem = (size_t)kChainWarps * kRing * 64 * NR;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_sgm_paths<NR, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
     }
-#undef SISTER_SELECT_CASE
+    const long long n = chain_count(d);
+    k_sgm_paths<NR, FULL><<<(unsigned)((n + kChainWarps - 1) / kChainWarps), kChainWarps * 32, smem, st>>>(fused, d, qvol);
+}
+
+void launch_sgm(const uint8_t *fused, const Dims &d, uint8_t *qvol, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
+                int *status, cudaStream_t st, LaunchCounter &lc)
+{
+    (void)status;
+    const int nr = (d.D + 63) / 64; // disparities per lane = 2 * NR, chosen so that D fits in 32 lanes
+    const bool full = d.D == 64 * nr;
+#define SISTER_PATHS_CASE(N)                                                                    \
+    case N:                                                                                     \
+        if (full) launch_paths<N, true>(fused, d, qvol, st);                                    \
+        else launch_paths<N, false>(fused, d, qvol, st);                                        \
+        break;
+    switch (nr) {
+        SISTER_PATHS_CASE(1) SISTER_PATHS_CASE(2) SISTER_PATHS_CASE(3) SISTER_PATHS_CASE(4)
+        SISTER_PATHS_CASE(5) SISTER_PATHS_CASE(6) SISTER_PATHS_CASE(7)
+    default:
+        if (full) launch_paths<8, true>(fused, d, qvol, st);
+        else launch_paths<8, false>(fused, d, qvol, st);
+        break;
+    }
+#undef SISTER_PATHS_CASE
+    lc.add();
+    const long long groups = (d.px + 3) / 4;
+    long long blocks = (groups + 7) / 8;
+    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    k_sgm_final<<<(unsigned)blocks, 256, 0, st>>>(fused, qvol, d, sum, raw_disp, out);
     lc.add();
 }
 

@@ -17,6 +17,7 @@ def engine():
     if not os.path.exists(sister_b200.library_path()):
         sister_b200.build_library()
     eng = sister_b200.Engine(256, 256, 64, n_slots=3)
+    eng.set_test_taps(True)
     yield eng
     eng.close()
 
