@@ -193,92 +193,161 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
 
 // ---------------------------------------------------------------------------------------------- fuse
 
-// Block = T x T image tile. For each view the tile's matching partners are T view-frame lines of
-// (T + D - 1) consecutive census codes; they are staged in shared memory once and every (pixel, d) cell of the
-// tile is evaluated from there. One warp per pixel at a time, lanes over d, byte stores coalesced along d.
-// grid (ceil(Wp/T), ceil(Hp/T)), block 256, dynamic smem 4 * T * (T + D) u64
-__global__ void __launch_bounds__(256) k_fuse(const unsigned long long *__restrict__ census, const uint8_t *__restrict__ masks,
-                                              Dims d, unsigned view_mask, int T, uint8_t *__restrict__ fused, int *__restrict__ status)
+// Block = T x T image tile, T warps; warp w owns tile row w and walks its T pixels. For each view the tile's matching
+// partners are T view-frame lines of (T + D - 1) consecutive census codes; they are staged in shared memory once
+// (views whose mask is 0 on the whole tile are skipped) and every (pixel, d) cell of the tile is evaluated from
+// there: lanes over d (d = lane + 32k), consecutive lanes read consecutive 8-byte codes (conflict-free), the D cost
+// bytes of a pixel leave as full 32-byte sectors.
+// Fast path (the only one the masks ever select, see the header comment): the view row is an ordinary census row and
+// the view column is >= D - 1, so every d has a partner and the cost is a plain popcount. Anything else takes the
+// literal per-cell formula of census.cpp:63-88,95-98 / hpp:264-276 below.
+// grid (ceil(Wp/T), ceil(Hp/T)), block 32 * T, dynamic smem 4 * T * (T + D) u64 + T * T bytes
+template <int T, int NK> // NK = D / 32 when D is a multiple of 32 (fully unrolled), 0 = any D
+__global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__restrict__ census, const uint8_t *__restrict__ masks,
+                                                 Dims d, unsigned view_mask, uint8_t *__restrict__ fused, int *__restrict__ status)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned s_any;
     unsigned long long *s = reinterpret_cast<unsigned long long *>(smem_raw);
     const int D = d.D, P = T + D; // line pitch (T + D - 1 used)
+    uint8_t *smask = smem_raw + (size_t)4 * T * P * 8;
     const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
-    const int tid = threadIdx.x;
-    int cv_lo[4] = {j0, d.Wp - j0 - T, d.Hp - i0 - T, i0};
+    const int tid = threadIdx.x, nthr = 32 * T;
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    {
+        unsigned mine = 0;
+        for (int e = tid; e < T * T; e += nthr) {
+            const int i = i0 + e / T, j = j0 + e % T;
+            unsigned m = 0;
+            if (i < d.Hp && j < d.Wp) {
+                const size_t pix = (size_t)i * d.Wp + j;
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+                    if (((view_mask >> v) & 1u) && masks[(size_t)v * d.px + pix]) m |= 1u << v;
+            }
+            smask[e] = (uint8_t)m;
+            mine |= m;
+        }
+        if (mine) atomicOr(&s_any, mine);
+    }
+    __syncthreads();
+    const unsigned any = s_any;
+    const int cv_lo[4] = {j0, d.Wp - j0 - T, d.Hp - i0 - T, i0};
+#pragma unroll
     for (int v = 0; v < 4; v++) {
-        if (!((view_mask >> v) & 1u)) continue;
+        if (!((any >> v) & 1u)) continue;
         const int hv = view_rows(d, v), wv = view_cols(d, v);
         const unsigned long long *c2 = census + (size_t)(2 * v + 1) * d.px;
         unsigned long long *sv = s + (size_t)v * T * P;
-        const int n = T * (P - 1);
-        for (int e = tid; e < n; e += blockDim.x) {
-            const int line = e / (P - 1), x = e % (P - 1);
-            const int rv = (v < 2) ? i0 + line : d.Wp - 1 - (j0 + line);
-            const int col = cv_lo[v] - (D - 1) + x;
-            unsigned long long val = 0;
-            if (rv >= 0 && rv < hv && col >= 0 && col < wv) val = c2[(size_t)rv * wv + col];
-            sv[line * P + x] = val;
+        // warp w stages line w: consecutive lanes, consecutive codes
+        const int line = tid >> 5;
+        const int rv = (v < 2) ? i0 + line : d.Wp - 1 - (j0 + line);
+        const bool row_ok = rv >= 0 && rv < hv;
+        const unsigned long long *src = c2 + (size_t)(row_ok ? rv : 0) * wv;
+        const int col0 = cv_lo[v] - (D - 1);
+        for (int x = tid & 31; x < P - 1; x += 32) {
+            const int col = col0 + x;
+            sv[line * P + x] = (row_ok && col >= 0 && col < wv) ? __ldg(src + col) : 0ull;
         }
     }
     __syncthreads();
-    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int lane = tid & 31, li = tid >> 5;
+    const int i = i0 + li;
+    if (i >= d.Hp) return;
+    constexpr int NKC = NK > 0 ? NK : 16;
     bool overflow = false;
-    for (int pidx = warp; pidx < T * T; pidx += nwarps) {
-        const int li = pidx / T, lj = pidx % T;
-        const int i = i0 + li, j = j0 + lj;
-        if (i >= d.Hp || j >= d.Wp) continue;
+#pragma unroll 1
+    for (int lj = 0; lj < T; lj++) {
+        const int j = j0 + lj;
+        if (j >= d.Wp) break;
         const size_t pix = (size_t)i * d.Wp + j;
-        // per-view setup (warp-uniform)
-        unsigned long long c1[4];
-        int e0[4], cv[4], kind[4]; // kind 0: skip, 1: popc, 2: all 255, 3: all 0
-        const unsigned long long *line_ptr[4];
+        const unsigned m = smask[li * T + lj];
+        unsigned acc[NKC];
+#pragma unroll
+        for (int k = 0; k < NKC; k++) acc[k] = 0;
 #pragma unroll
         for (int v = 0; v < 4; v++) {
-            kind[v] = 0; c1[v] = 0; e0[v] = 0; cv[v] = 0; line_ptr[v] = s;
-            if (!((view_mask >> v) & 1u)) continue;
-            if (!masks[(size_t)v * d.px + pix]) continue;
+            if (!((m >> v) & 1u)) continue; // warp-uniform
             const int hv = view_rows(d, v), wv = view_cols(d, v);
             int rv, cc;
             image_to_view(d, v, i, j, rv, cc);
-            cv[v] = cc;
-            if (rv < 3) kind[v] = 2;              // census.cpp:95-98,142-145
-            else if (rv >= hv - 2) kind[v] = 3;   // never written by the reference: defined 0
-            else {
-                kind[v] = 1;
-                c1[v] = census[(size_t)(2 * v) * d.px + (size_t)rv * wv + cc];
-                e0[v] = cc - cv_lo[v] + D - 1;
-                line_ptr[v] = s + (size_t)v * T * P + (size_t)((v < 2) ? li : lj) * P;
+            const unsigned long long *line = s + (size_t)v * T * P + (size_t)((v < 2) ? li : lj) * P + (cc - cv_lo[v] + D - 1);
+            if (rv >= 3 && rv < hv - 2 && cc >= D - 1) {
+                const unsigned long long c1 = __ldg(census + (size_t)(2 * v) * d.px + (size_t)rv * wv + cc);
+                const unsigned c1lo = (unsigned)c1, c1hi = (unsigned)(c1 >> 32);
+                const unsigned long long *p = line - lane;
+#pragma unroll
+                for (int k = 0; k < NKC; k++) {
+                    if (NK > 0 || lane + 32 * k < D) {
+                        const uint2 x = *reinterpret_cast<const uint2 *>(p - 32 * k);
+                        acc[k] += __popc(x.x ^ c1lo) + __popc(x.y ^ c1hi);
+                    }
+                }
+            } else {
+                // literal formula: rows 0..2 are 255 (census.cpp:95-98,142-145), rows h-2,h-1 are never written
+                // (defined 0), d beyond the view column is 255 (census.cpp:76)
+                unsigned long long c1 = 0;
+                const bool popc_row = rv >= 3 && rv < hv - 2;
+                if (popc_row) c1 = __ldg(census + (size_t)(2 * v) * d.px + (size_t)rv * wv + cc);
+#pragma unroll 1
+                for (int k = 0; k < NKC; k++) {
+                    const int dd = lane + 32 * k;
+                    if (dd >= D) break;
+                    unsigned cst;
+                    if (rv < 3) cst = kInvalidCost;
+                    else if (!popc_row) cst = 0;
+                    else cst = (dd > cc) ? (unsigned)kInvalidCost : (unsigned)__popcll(c1 ^ line[-dd]);
+                    acc[k] += cst;
+                }
             }
         }
-        uint8_t *dst = fused + pix * D;
-        for (int dd = lane; dd < D; dd += 32) {
-            unsigned sum = 0;
+        uint8_t *dst = fused + pix * D + lane;
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
-                if (kind[v] == 1) sum += (dd > cv[v]) ? (unsigned)kInvalidCost : (unsigned)__popcll(c1[v] ^ line_ptr[v][e0[v] - dd]);
-                else if (kind[v] == 2) sum += kInvalidCost;
+        for (int k = 0; k < NKC; k++) {
+            if (NK > 0 || lane + 32 * k < D) {
+                unsigned sum = acc[k];
+                if (sum > 255u) { overflow = true; sum = 255u; }
+                dst[32 * k] = (uint8_t)sum;
             }
-            if (sum > 255u) { overflow = true; sum = 255u; }
-            dst[dd] = (uint8_t)sum;
         }
     }
     if (overflow) atomicOr(status, kStatusFusedOverflow);
 }
 
-void launch_fuse(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
-                 int *status, cudaStream_t st, LaunchCounter &lc)
+template <int T, int NK>
+static void launch_fuse_t(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
+                          int *status, cudaStream_t st)
 {
-    int T = 16;
-    while (T > 4 && (size_t)4 * T * (T + d.D) * 8 > 200 * 1024) T /= 2;
-    size_t smem = (size_t)4 * T * (T + d.D) * 8;
+    const size_t smem = (size_t)4 * T * (T + d.D) * 8 + T * T;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_fuse, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_fuse<T, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_done = true;
     }
     dim3 grid((d.Wp + T - 1) / T, (d.Hp + T - 1) / T);
-    k_fuse<<<grid, 256, smem, st>>>(census, masks, d, view_mask, T, fused, status);
+    k_fuse<T, NK><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, status);
+}
+
+void launch_fuse(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
+                 int *status, cudaStream_t st, LaunchCounter &lc)
+{
+    // 16 x 16 tiles while two blocks fit an SM (D <= 200), else 8 x 8
+    if (d.D <= 200) {
+        switch (d.D) {
+        case 64: launch_fuse_t<16, 2>(census, masks, d, view_mask, fused, status, st); break;
+        case 128: launch_fuse_t<16, 4>(census, masks, d, view_mask, fused, status, st); break;
+        case 192: launch_fuse_t<16, 6>(census, masks, d, view_mask, fused, status, st); break;
+        default: launch_fuse_t<16, 0>(census, masks, d, view_mask, fused, status, st); break;
+        }
+    } else {
+        switch (d.D) {
+        case 256: launch_fuse_t<8, 8>(census, masks, d, view_mask, fused, status, st); break;
+        case 384: launch_fuse_t<8, 12>(census, masks, d, view_mask, fused, status, st); break;
+        case 512: launch_fuse_t<8, 16>(census, masks, d, view_mask, fused, status, st); break;
+        default: launch_fuse_t<8, 0>(census, masks, d, view_mask, fused, status, st); break;
+        }
+    }
     lc.add();
 }
 
