@@ -80,6 +80,7 @@ int check_shape(sister_ctx *ctx, int w, int h, int D, Dims &d)
     d.W = w; d.H = h; d.D = D; d.Wp = w + 2 * D; d.Hp = h + 2 * D;
     d.px = (long long)d.Wp * d.Hp;
     d.cells = d.px * D;
+    if (d.cells / 8 > 0x7F000000LL) { ctx->err = "cost volume above 1.7e10 cells (32-bit cursor offsets in sgm.cu)"; return SISTER_E_SHAPE; }
     if (w > ctx->max_w || h > ctx->max_h || D > ctx->max_d || d.px > ctx->px_max || d.cells > ctx->cells_max) {
         ctx->err = "rig larger than the capacity given to sister_create";
         return SISTER_E_CAPACITY;
@@ -519,7 +520,7 @@ int sister_debug_fetch(sister_ctx *ctx, int slot, int what, void *host_dst, size
 int sister_test_sgm(sister_ctx *ctx, const uint8_t *fused, int w, int h, int disp_count, uint16_t *sum, int16_t *disp)
 {
     if (!ctx || !fused || !sum) return SISTER_E_ARG;
-    if (disp_count <= 0 || disp_count % 8 != 0 || disp_count > 512 || w < 2 || h < 2) { ctx->err = "bad sgm test shape"; return SISTER_E_SHAPE; }
+    if (disp_count <= 0 || disp_count % 8 != 0 || disp_count > 512 || w < 12 || h < 12) { ctx->err = "bad sgm test shape"; return SISTER_E_SHAPE; }
     Dims d;
     d.W = 0; d.H = 0; d.D = disp_count; d.Wp = w; d.Hp = h;
     d.px = (long long)w * h;

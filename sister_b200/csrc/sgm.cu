@@ -189,114 +189,193 @@ __device__ __forceinline__ bool chain_decode(const Dims &d, long long g, Chain &
 
 // ---------------------------------------------------------------------------------------------- the path kernel
 
+// store the step's penalty bytes (q <= 255 in both halves): 2 * NR bytes per lane
+template <int NR, bool FULL> __device__ __forceinline__ void store_q(uint8_t *dst, const uint32_t (&q)[NR], int nvalid)
+{
+    if constexpr (NR % 2 == 0) {
+        // lane * 2NR is a multiple of 4 and cell * D a multiple of 8: 32-bit stores are always aligned
+        if (FULL || nvalid == NR) {
+            uint32_t w[NR / 2];
+#pragma unroll
+            for (int k = 0; k < NR / 2; k++) w[k] = __byte_perm(q[2 * k], q[2 * k + 1], 0x6420);
+            if constexpr (FULL && NR == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+            else if constexpr (FULL && NR == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            else {
+#pragma unroll
+                for (int k = 0; k < NR / 2; k++) reinterpret_cast<uint32_t *>(dst)[k] = w[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NR; k++)
+                if (k < nvalid) reinterpret_cast<uint16_t *>(dst)[k] = (uint16_t)__byte_perm(q[k], 0u, 0x4420);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NR; k++)
+            if (FULL || k < nvalid) reinterpret_cast<uint16_t *>(dst)[k] = (uint16_t)__byte_perm(q[k], 0u, 0x4420);
+    }
+}
+
+// Per-warp view of one chain: cursors are 32-bit offsets in units of 8 bytes (D % 8 == 0) from the volume base, turned
+// into addresses with one IMAD.WIDE; the cost ring is kRing slots of 64 * NR bytes.
+template <int NR, bool FULL> struct ChainRun {
+    static constexpr int kSlotBytes = 64 * NR;
+    static constexpr unsigned kRingBytes = kRing * kSlotBytes;
+    const uint8_t *fused_lane; // fused + lane * 8
+    uint8_t *q_lane;           // path volume + lane * 2NR
+    unsigned ring_ld;          // shared address of the ring + lane * 2NR (reads)
+    unsigned ring_st;          // shared address of the ring + lane * 8   (cp.async destination)
+    int lane, nvalid;
+    bool ld0, ld1;
+    unsigned rd_off = 0;                           // ring slot of the step being consumed
+    unsigned wr_off = (kRing - 1) * kSlotBytes;    // free slot: the one consumed in the previous step
+
+    __device__ __forceinline__ void issue(unsigned slot_off, int off8) const
+    {
+        const uint8_t *src = fused_lane + (long long)off8 * 8;
+        if (ld0) cp_async8(ring_st + slot_off, src);
+        if (NR > 4 && ld1) cp_async8(ring_st + slot_off + 256, src + 256);
+    }
+    __device__ __forceinline__ void consume(uint32_t (&c)[NR]) const
+    {
+        cp_async_wait<kRing - 2>();
+        __syncwarp();
+        const unsigned src = ring_ld + rd_off;
+#pragma unroll
+        for (int k = 0; k < NR; k++) {
+            unsigned short v;
+            asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(src + 2 * k) : "memory");
+            c[k] = __byte_perm((uint32_t)v, 0u, 0x4140);
+        }
+    }
+    // returns the free slot (consumed one step ago, every lane is past its reads: a __syncwarp lies in between),
+    // frees the slot consumed in this step for the next one and moves on
+    __device__ __forceinline__ unsigned advance_ring()
+    {
+        const unsigned free_slot = wr_off;
+        wr_off = rd_off;
+        rd_off = (rd_off + kSlotBytes == kRingBytes) ? 0u : rd_off + kSlotBytes;
+        return free_slot;
+    }
+};
+
 // grid ceil(chain_count / kChainWarps), block kChainWarps * 32, dynamic smem kChainWarps * kRing * 64 * NR bytes
 template <int NR, bool FULL>
 __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, uint8_t *__restrict__ qvol)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int kSlotBytes = 64 * NR;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Chain ch;
     if (!chain_decode(d, (long long)blockIdx.x * kChainWarps + warp, ch)) return;
     const int D = d.D, Wp = d.Wp;
-    const int nvalid = FULL ? NR : lane_nvalid<NR>(D, lane);
+    using Run = ChainRun<NR, FULL>;
+    Run run;
+    run.lane = lane;
+    run.nvalid = FULL ? NR : lane_nvalid<NR>(D, lane);
+    run.ld0 = lane * 8 < D;
+    run.ld1 = lane * 8 + 256 < D;
+    run.fused_lane = fused + lane * 8;
+    run.q_lane = qvol + (size_t)ch.vol * (size_t)d.cells + lane * 2 * NR;
+    {
+        const unsigned base = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)warp * Run::kRingBytes);
+        run.ring_ld = base + lane * 2 * NR;
+        run.ring_st = base + lane * 8;
+    }
+    const int nvalid = run.nvalid;
+    const int D8 = D >> 3;
+    // a chain advances by a constant offset; a diagonal chain that steps over a side border re-enters at the opposite
+    // one (same row), a fixed correction of one row of cells
+    const int stride8 = (ch.si * Wp + ch.sj) * D8;
+    const int wrapfix8 = -ch.sj * Wp * D8;
+    const int first8 = (ch.i * Wp + ch.j) * D8;
+    const int nsteps = ch.nsteps;
 
-    // Cursors advance by a constant byte stride; a diagonal chain that steps over a side border re-enters at the
-    // opposite one (same row), which is a fixed correction of one row of cells.
-    const long long stride = ((long long)ch.si * Wp + ch.sj) * D;
-    const long long wrapfix = -(long long)ch.sj * Wp * D;
-    const size_t first_cell = ((size_t)ch.i * Wp + ch.j) * D;
-    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)warp * kRing * kSlotBytes);
-    constexpr unsigned kRingBytes = kRing * kSlotBytes;
-
-    // prefetch cursor: lane l fetches bytes [8l, 8l+8) and [8l+256, 8l+264) of the cell's D cost bytes
-    const uint8_t *psrc = fused + first_cell + lane * 8;
-    int pj = ch.j;
-    const bool ld0 = lane * 8 < D, ld1 = lane * 8 + 256 < D;
-    auto issue = [&](unsigned slot_off) {
-        if (ld0) cp_async8(ring_s + slot_off + lane * 8, psrc);
-        if (NR > 4 && ld1) cp_async8(ring_s + slot_off + lane * 8 + 256, psrc + 256);
-    };
-    auto padvance = [&]() {
-        psrc += stride; pj += ch.sj;
-        if ((unsigned)pj >= (unsigned)Wp) { pj = ch.enter; psrc += wrapfix; }
-    };
+    // prologue: kRing - 1 steps in flight
+    int poff = first8, pj = ch.j;
+    const bool diag = ch.kind == 2 && ch.sj != 0;
 #pragma unroll 1
     for (int t = 0; t < kRing - 1; t++) {
-        if (t < ch.nsteps) issue(t * kSlotBytes);
+        run.issue(t * Run::kSlotBytes, poff); // nsteps >= 16 > kRing (check_shape)
         cp_async_commit();
-        padvance();
+        poff += stride8;
+        if (diag) { pj += ch.sj; if ((unsigned)pj >= (unsigned)Wp) { pj = ch.enter; poff += wrapfix8; } }
     }
 
     uint32_t a[NR], c[NR], q[NR];
+    if (ch.kind == 1) {
+        // ---- r0 on the first line of the pass: un-normalised, truncated state (sgm.cpp:141-190) ----
+        unsigned m = 0;
 #pragma unroll
-    for (int k = 0; k < NR; k++) a[k] = (k < nvalid) ? 0u : kInf2; // r0 at the start of a row (sgm.cpp:215-216)
-    unsigned m_first = 0;
-    uint8_t *qdst = qvol + (size_t)ch.vol * (size_t)d.cells + first_cell + lane * 2 * NR;
-    int j = ch.j;
-    unsigned rd_off = 0, wr_off = (kRing - 1) * kSlotBytes;
-    int to_issue = ch.nsteps - (kRing - 1);
-    bool reset = false;
+        for (int k = 0; k < NR; k++) a[k] = kInf2;
+        uint8_t *qlag = run.q_lane - (long long)(kRing - 1) * stride8 * 8;
 #pragma unroll 1
-    for (int s = 0; s < ch.nsteps; s++) {
-        cp_async_wait<kRing - 2>();
-        __syncwarp();
-        {
-            const unsigned src = ring_s + rd_off + lane * 2 * NR;
-#pragma unroll
-            for (int k = 0; k < NR; k++) {
-                unsigned short v;
-                asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(src + 2 * k) : "memory");
-                c[k] = __byte_perm((uint32_t)v, 0u, 0x4140);
-            }
+        for (int s = 0; s < nsteps; s++) {
+            run.consume(c);
+            const unsigned wr = run.advance_ring();
+            if (s < nsteps - (kRing - 1)) run.issue(wr, poff);
+            cp_async_commit();
+            first_line_step<NR, FULL>(a, m, c, lane, nvalid, s == 0, q);
+            store_q<NR, FULL>(qlag + (long long)poff * 8, q, nvalid);
+            poff += stride8;
         }
-        if (to_issue > 0) issue(wr_off);
-        to_issue--;
-        cp_async_commit();
-        padvance();
-
-        if (ch.kind == 1) {
-            first_line_step<NR, FULL>(a, m_first, c, lane, nvalid, s == 0, q);
-        } else if (ch.kind == 2 && s == 0) {
+    } else if (!diag) {
+        // ---- rows (r0, a = 0 at the start of the row, sgm.cpp:215-216) and columns (r2): no border crossing ----
+        // the store cursor is the prefetch cursor kRing - 1 steps ago: fold the lag into the base pointer
+        uint8_t *qlag = run.q_lane - (long long)(kRing - 1) * stride8 * 8;
+        int s = 0;
+        if (ch.kind == 2) {
+            run.consume(c);
+            const unsigned wr = run.advance_ring();
+            run.issue(wr, poff);
+            cp_async_commit();
             chain_first_cell<NR, FULL>(a, c, nvalid, q);
+            store_q<NR, FULL>(qlag + (long long)poff * 8, q, nvalid);
+            poff += stride8;
+            s = 1;
         } else {
-            if (reset) {
 #pragma unroll
-                for (int k = 0; k < NR; k++) a[k] = (FULL || k < nvalid) ? kP2x2 : kInf2; // sgm.cpp:57-81
-            }
+            for (int k = 0; k < NR; k++) a[k] = (k < nvalid) ? 0u : kInf2;
+        }
+        const int n_issue = nsteps - (kRing - 1);
+#pragma unroll 1
+        for (; s < nsteps; s++) {
+            run.consume(c);
+            const unsigned wr = run.advance_ring();
+            if (s < n_issue) run.issue(wr, poff);
+            cp_async_commit();
             chain_step<NR, FULL>(a, c, lane, nvalid, q);
+            store_q<NR, FULL>(qlag + (long long)poff * 8, q, nvalid);
+            poff += stride8;
         }
-
-        // one byte per cell: q <= 255 in both halves
-        uint8_t *dst = qdst;
-        if constexpr (NR % 2 == 0) {
-            // lane * 2NR is a multiple of 4 and pix * D a multiple of 8: 32-bit stores are always aligned
-            if (FULL || nvalid == NR) {
-                uint32_t w[NR / 2];
+    } else {
+        // ---- diagonals (r1, r3): wrapped chains, a = P2 after a border crossing (sgm.cpp:57-81) ----
+        int qoff = first8, j = ch.j;
+        {
+            run.consume(c);
+            const unsigned wr = run.advance_ring();
+            run.issue(wr, poff);
+            cp_async_commit();
+            chain_first_cell<NR, FULL>(a, c, nvalid, q);
+            store_q<NR, FULL>(run.q_lane + (long long)qoff * 8, q, nvalid);
+        }
+        const int n_issue = nsteps - (kRing - 1);
+#pragma unroll 1
+        for (int s = 1; s < nsteps; s++) {
+            poff += stride8; pj += ch.sj;
+            if ((unsigned)pj >= (unsigned)Wp) { pj = ch.enter; poff += wrapfix8; }
+            qoff += stride8; j += ch.sj;
+            if ((unsigned)j >= (unsigned)Wp) {
+                j = ch.enter; qoff += wrapfix8;
 #pragma unroll
-                for (int k = 0; k < NR / 2; k++) w[k] = __byte_perm(q[2 * k], q[2 * k + 1], 0x6420);
-                if constexpr (FULL && NR == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
-                else if constexpr (FULL && NR == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-                else {
-#pragma unroll
-                    for (int k = 0; k < NR / 2; k++) reinterpret_cast<uint32_t *>(dst)[k] = w[k];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < NR; k++)
-                    if (k < nvalid) reinterpret_cast<uint16_t *>(dst)[k] = (uint16_t)__byte_perm(q[k], 0u, 0x4420);
+                for (int k = 0; k < NR; k++) a[k] = (FULL || k < nvalid) ? kP2x2 : kInf2;
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < NR; k++)
-                if (FULL || k < nvalid) reinterpret_cast<uint16_t *>(dst)[k] = (uint16_t)__byte_perm(q[k], 0u, 0x4420);
+            run.consume(c);
+            const unsigned wr = run.advance_ring();
+            if (s < n_issue) run.issue(wr, poff);
+            cp_async_commit();
+            chain_step<NR, FULL>(a, c, lane, nvalid, q);
+            store_q<NR, FULL>(run.q_lane + (long long)qoff * 8, q, nvalid);
         }
-
-        qdst += stride; j += ch.sj;
-        reset = (unsigned)j >= (unsigned)Wp;
-        if (reset) { j = ch.enter; qdst += wrapfix; }
-        rd_off = (rd_off + kSlotBytes == kRingBytes) ? 0u : rd_off + kSlotBytes;
-        wr_off = (wr_off + kSlotBytes == kRingBytes) ? 0u : wr_off + kSlotBytes;
     }
     cp_async_wait<0>();
 }
