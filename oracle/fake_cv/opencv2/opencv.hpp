@@ -47,10 +47,19 @@ struct Rect {
 class Mat;
 struct MatExpr;
 
+// cv::MatStep: converts to size_t (bytes between rows), like the real one
+struct MatStep {
+    size_t v = 0;
+    operator size_t() const { return v; }
+    size_t operator[](int) const { return v; }
+    MatStep &operator=(size_t s) { v = s; return *this; }
+};
+
 class Mat {
 public:
     int rows = 0, cols = 0;
     uchar *data = nullptr;
+    MatStep step;
 
     Mat() {}
     Mat(int r, int c, int t) { create(r, c, t); }
@@ -60,7 +69,7 @@ public:
     void create(int r, int c, int t)
     {
         rows = r; cols = c; type_ = t;
-        step_ = (size_t)c * fakecv_elem_size(t);
+        step = (size_t)c * fakecv_elem_size(t);
         // The reference's dead "consensus" loop (hpp:91-109) indexes (cols x rows)-shaped Mats with
         // (row<rows', col<cols') of the transposed shape; give every buffer max(r,c)^2 elements of
         // zeroed slack so that stays inside the allocation for portrait frames too.
@@ -74,17 +83,18 @@ public:
     }
     int type() const { return type_; }
     bool empty() const { return data == nullptr; }
-    size_t step() const { return step_; }
+    int channels() const { return type_ == CV_8UC3 ? 3 : 1; }
+    bool isContinuous() const { return (size_t)step == (size_t)cols * fakecv_elem_size(type_); }
 
-    template <typename T> T &at(int i, int j) { return *(T *)(data + (size_t)i * step_ + (size_t)j * sizeof(T)); }
-    template <typename T> const T &at(int i, int j) const { return *(const T *)(data + (size_t)i * step_ + (size_t)j * sizeof(T)); }
+    template <typename T> T &at(int i, int j) { return *(T *)(data + (size_t)i * step.v + (size_t)j * sizeof(T)); }
+    template <typename T> const T &at(int i, int j) const { return *(const T *)(data + (size_t)i * step.v + (size_t)j * sizeof(T)); }
 
     // ROI view sharing storage (hpp:116-118).
     Mat operator()(const Rect &r) const
     {
         Mat m;
-        m.rows = r.height; m.cols = r.width; m.type_ = type_; m.step_ = step_; m.store_ = store_;
-        m.data = data + (size_t)r.y * step_ + (size_t)r.x * fakecv_elem_size(type_);
+        m.rows = r.height; m.cols = r.width; m.type_ = type_; m.step = step; m.store_ = store_;
+        m.data = data + (size_t)r.y * step.v + (size_t)r.x * fakecv_elem_size(type_);
         return m;
     }
 
@@ -106,7 +116,6 @@ public:
 
 private:
     int type_ = 0;
-    size_t step_ = 0;
     std::shared_ptr<uchar> store_;
 };
 
@@ -140,7 +149,7 @@ inline void cvtColor(const Mat &src, Mat &dst, int code)
     if (src.empty()) throw std::runtime_error("fake cv: empty input");
     Mat out(src.rows, src.cols, CV_8UC1);
     for (int i = 0; i < src.rows; i++) {
-        const uchar *p = src.data + (size_t)i * src.step();
+        const uchar *p = src.data + (size_t)i * (size_t)src.step;
         for (int j = 0; j < src.cols; j++) {
             int b = p[3 * j], g = p[3 * j + 1], r = p[3 * j + 2];
             out.at<uchar>(i, j) = (uchar)((3735 * b + 19235 * g + 9798 * r + 16384) >> 15);

@@ -69,7 +69,7 @@ struct StdoutMute {
 cv::Mat wrap_bgr(const uint8_t *p, int w, int h)
 {
     cv::Mat m(h, w, cv::CV_8UC3);
-    for (int i = 0; i < h; i++) std::memcpy(m.data + (size_t)i * m.step(), p + (size_t)i * w * 3, (size_t)w * 3);
+    for (int i = 0; i < h; i++) std::memcpy(m.data + (size_t)i * (size_t)m.step, p + (size_t)i * w * 3, (size_t)w * 3);
     return m;
 }
 
@@ -91,9 +91,9 @@ int ref_compute_disparities(const uint8_t *const *views_bgr, int w, int h, int d
         s.compute_disparities(disp_count, mv, hz, vt);
         if (mv.rows != h || mv.cols != w) return -2;
         for (int i = 0; i < h; i++) {
-            std::memcpy(out_mv + (size_t)i * w, mv.data + (size_t)i * mv.step(), (size_t)w * 2);
-            std::memcpy(out_h + (size_t)i * w, hz.data + (size_t)i * hz.step(), (size_t)w * 2);
-            std::memcpy(out_v + (size_t)i * w, vt.data + (size_t)i * vt.step(), (size_t)w * 2);
+            std::memcpy(out_mv + (size_t)i * w, mv.data + (size_t)i * (size_t)mv.step, (size_t)w * 2);
+            std::memcpy(out_h + (size_t)i * w, hz.data + (size_t)i * (size_t)hz.step, (size_t)w * 2);
+            std::memcpy(out_v + (size_t)i * w, vt.data + (size_t)i * (size_t)vt.step, (size_t)w * 2);
         }
         return 0;
     } catch (...) {
