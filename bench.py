@@ -207,12 +207,14 @@ def main():
     evals = cost_evals(W_, H_, D_)
     cells = (W_ + 2 * D_) * (H_ + 2 * D_) * D_
 
-    # ---- synthetic rigs: distinct seeds per rank and per rig ----
-    rigs_bgr = [make_rig(W_, H_, D_, seed=1234 + rank * B + k, channels=3) for k in range(B)]
+    # ---- synthetic rigs: the job is world * B rigs, sharded by frame (sister_b200/sharding.py); seeds follow the global
+    # rig index ----
+    from sister_b200.sharding import frame_shard, gather_maps
+    g0, g1 = frame_shard(world * B, world, rank)
+    rigs_bgr = [make_rig(W_, H_, D_, seed=1234 + g, channels=3) for g in range(g0, g1)]
     # device-resident copies (torch owns the memory; the C ABI takes raw device pointers)
     rig_t = [torch.from_numpy(np.stack(r)).to(dev) for r in rigs_bgr]          # B x [5, H, W, 3] uint8
     out_t = torch.zeros((B, H_, W_), dtype=torch.int16, device=dev)  # uint16 bit patterns (NCCL has no u16)
-    gather_t = [torch.zeros_like(out_t) for _ in range(world)] if (world > 1 and rank == 0) else None
     torch.cuda.synchronize()
 
     def barrier():
@@ -228,7 +230,7 @@ def main():
     def gather_step():
         if world > 1:
             eng.sync()
-            dist.gather(out_t, gather_t, dst=0)
+            gather_maps(out_t, world * B, dst=0)
 
     # ---- value: device-resident, device-timed ----
     for _ in range(args.warmup):
