@@ -18,9 +18,103 @@ namespace sister {
 
 // ---------------------------------------------------------------------------------------------- WTA L/R
 
-// grid (max(hv), 4), block 256, dynamic smem: 2 * wv u64 + wv u32
-__global__ void __launch_bounds__(256) k_match_wta(const unsigned long long *__restrict__ census, Dims d, unsigned view_mask,
-                                                   int16_t *__restrict__ wtaL, int16_t *__restrict__ wtaR)
+constexpr unsigned kNoKey = 0xFFFFFFFFu;
+constexpr int kMatchK = 4; // consecutive view columns per lane
+
+// One pass over the (a, d) pairs of a block of 32 * K view columns a = A + lane * K + k, d = 0 .. D-1.
+// Every pair's Hamming cost popc64(c1[a] ^ c2[a - d]) is evaluated ONCE and feeds both reductions as the key
+// (cost << 16) | d, whose minimum is the first-index argmin of WTALeft_SSE / WTARight_SSE (postprocess.cpp:74-315,
+// uniqueness test dead at 1.0):
+//   left map  L[a]: the lane's own running minimum over d;
+//   right map R[b], b = a - d: a systolic accumulator that travels with b. At step d a lane's K columns meet the K
+//     partners b = a0 - d .. a0 - d + K - 1; one step later that window has slid down by one, so the top partner (its
+//     census code and its accumulator) moves to the next lane by one shuffle, lane 0 takes a new partner from shared
+//     memory and lane 31 retires one accumulator into rkey[] with a shared-memory atomicMin. The window is a rotating
+//     register file (slot (k - s) mod K at sub-step s = d mod K), so nothing else moves.
+// CHECK = false when every pair of the block is in range (A >= D - 1 and A + 32K <= wv).
+__device__ __forceinline__ void red_min_shared_if(unsigned addr, unsigned val, bool pred)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.min.u32 [%0], %1;\n\t}\n" ::"r"(addr), "r"(val), "r"((unsigned)pred) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(unsigned addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
+template <int K, bool CHECK>
+__device__ __forceinline__ void match_block(unsigned c1_s, unsigned c2_s, unsigned rkey_s, int wv, int D, int A, int lane,
+                                            int16_t *__restrict__ outL)
+{
+    // c1_s, c2_s, rkey_s: shared-memory addresses of the row's census codes (8 bytes each) and of the R keys (4 bytes)
+    const int a0 = A + lane * K;
+    unsigned x1lo[K], x1hi[K], wlo[K], whi[K], racc[K], lkey[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const bool in = !CHECK || a0 + k < wv;
+        const uint2 x = in ? lds64(c1_s + 8u * (a0 + k)) : make_uint2(0u, 0u), y = in ? lds64(c2_s + 8u * (a0 + k)) : make_uint2(0u, 0u);
+        x1lo[k] = x.x; x1hi[k] = x.y;
+        wlo[k] = y.x; whi[k] = y.y;
+        racc[k] = kNoKey; lkey[k] = kNoKey;
+    }
+    const bool last_lane = lane == 31, first_lane = lane == 0;
+    // step dd: lane 31 retires rkey[a0 + K - dd], lane 0 takes c2[A - dd]; both walk down one element per step
+    unsigned top_s = rkey_s + 4u * (a0 + K); // minus 4 * dd
+    unsigned new_s = c2_s + 8u * A;          // minus 8 * dd
+#pragma unroll 1
+    for (int t = 0; t < D / K; t++) {
+#pragma unroll
+        for (int s = 0; s < K; s++) {
+            const int dd = t * K + s;
+            const int p = (K - s) % K; // slot of the partner that leaves the window / of the one that enters
+            if (s > 0 || t > 0) {
+                const int b_top = a0 - dd + K; // partner that was on top at step dd - 1
+                red_min_shared_if(top_s - 4u * s, racc[p], last_lane && (!CHECK || (b_top >= 0 && b_top < wv)));
+                uint2 y = make_uint2(0u, 0u);
+                if (!CHECK || A - dd >= 0) y = lds64(new_s - 8u * s); // warp-uniform address: one broadcast read
+                const unsigned slo = __shfl_up_sync(0xFFFFFFFFu, wlo[p], 1);
+                const unsigned shi = __shfl_up_sync(0xFFFFFFFFu, whi[p], 1);
+                const unsigned sac = __shfl_up_sync(0xFFFFFFFFu, racc[p], 1);
+                wlo[p] = first_lane ? y.x : slo;
+                whi[p] = first_lane ? y.y : shi;
+                racc[p] = first_lane ? kNoKey : sac;
+            }
+            const unsigned kd = (unsigned)dd;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int q = (k - s + K) % K;
+                unsigned key = (unsigned)__popc(x1lo[k] ^ wlo[q]) * 65536u + kd;
+                key = (unsigned)__popc(x1hi[k] ^ whi[q]) * 65536u + key;
+                if (CHECK && (a0 + k - dd < 0 || a0 + k >= wv)) key = kNoKey;
+                lkey[k] = min(lkey[k], key);
+                racc[q] = min(racc[q], key);
+            }
+        }
+        top_s -= 4u * K;
+        new_s -= 8u * K;
+    }
+    // retire what is still in the window: logical position e holds b = a0 - (D - 1) + e, slot (e - (K - 1)) mod K
+#pragma unroll
+    for (int e = 0; e < K; e++) {
+        const int b = a0 - (D - 1) + e;
+        const unsigned v = racc[(e - (K - 1) + K) % K];
+        red_min_shared_if(rkey_s + 4u * (unsigned)b, v, !CHECK || (b >= 0 && b < wv));
+    }
+    if (!CHECK) {
+        static_assert(K == 4, "the vector store below assumes 4 columns per lane");
+        short4 o = make_short4((short)(lkey[0] & 0xFFFFu), (short)(lkey[1] & 0xFFFFu), (short)(lkey[2] & 0xFFFFu), (short)(lkey[3] & 0xFFFFu));
+        *reinterpret_cast<short4 *>(outL + a0) = o; // a0 % 4 == 0 and wv % 4 == 0: 8-byte aligned
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (a0 + k < wv) outL[a0 + k] = (int16_t)(lkey[k] & 0xFFFFu);
+    }
+}
+
+// grid (max(hv), 4), block 32 * ceil(max(wv) / (32 K)) (at most 1024), dynamic smem: 2 * wv u64 + wv u32
+__global__ void __launch_bounds__(1024) k_match_wta(const unsigned long long *__restrict__ census, Dims d, unsigned view_mask,
+                                                    int16_t *__restrict__ wtaL, int16_t *__restrict__ wtaR)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int v = blockIdx.y, r = blockIdx.x;
@@ -41,28 +135,18 @@ __global__ void __launch_bounds__(256) k_match_wta(const unsigned long long *__r
     unsigned *rkey = reinterpret_cast<unsigned *>(c2 + wv);
     const unsigned long long *g1 = census + (size_t)(2 * v) * d.px + (size_t)r * wv;
     const unsigned long long *g2 = census + (size_t)(2 * v + 1) * d.px + (size_t)r * wv;
-    for (int c = tid; c < wv; c += blockDim.x) { c1[c] = g1[c]; c2[c] = g2[c]; rkey[c] = 0xFFFFFFFFu; }
+    for (int c = tid; c < wv; c += blockDim.x) { c1[c] = g1[c]; c2[c] = g2[c]; rkey[c] = kNoKey; }
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int D = d.D;
-    const int nblk = (wv + 31) / 32;
+    constexpr int kCols = 32 * kMatchK;
+    const int nblk = (wv + kCols - 1) / kCols;
+    const unsigned c1_s = (unsigned)__cvta_generic_to_shared(c1), c2_s = (unsigned)__cvta_generic_to_shared(c2);
+    const unsigned rkey_s = (unsigned)__cvta_generic_to_shared(rkey);
     for (int blk = warp; blk < nblk; blk += nwarps) {
-        const int A = blk * 32, a = A + lane;
-        const bool a_ok = a < wv;
-        const unsigned long long x1 = a_ok ? c1[a] : 0ull;
-        unsigned lkey = 0xFFFFFFFFu;
-        const int b_lo = max(0, A - D + 1), b_hi = min(A + 31, wv - 1);
-        for (int b = b_lo; b <= b_hi; b++) {
-            const unsigned long long x2 = c2[b]; // broadcast
-            const int dd = a - b;
-            const unsigned cost = __popcll(x1 ^ x2);
-            const bool ok = a_ok && dd >= 0 && dd < D;
-            const unsigned key = ok ? ((cost << 16) | (unsigned)dd) : 0xFFFFFFFFu;
-            lkey = min(lkey, key);
-            const unsigned rk = __reduce_min_sync(0xFFFFFFFFu, key);
-            if (lane == 0 && rk != 0xFFFFFFFFu) atomicMin(&rkey[b], rk);
-        }
-        if (a_ok) outL[a] = (int16_t)(lkey & 0xFFFFu);
+        const int A = blk * kCols;
+        if (A >= D - 1 && A + kCols <= wv) match_block<kMatchK, false>(c1_s, c2_s, rkey_s, wv, D, A, lane, outL);
+        else match_block<kMatchK, true>(c1_s, c2_s, rkey_s, wv, D, A, lane, outL);
     }
     __syncthreads();
     for (int c = tid; c < wv; c += blockDim.x) outR[c] = (int16_t)(rkey[c] & 0xFFFFu);
@@ -78,8 +162,10 @@ void launch_match_wta(const unsigned long long *census, const Dims &d, unsigned 
         cudaFuncSetAttribute(k_match_wta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
+    int warps = (m + 32 * kMatchK - 1) / (32 * kMatchK);
+    if (warps > 32) warps = 32;
     dim3 grid(m, 4);
-    k_match_wta<<<grid, 256, smem, st>>>(census, d, view_mask, wtaL, wtaR);
+    k_match_wta<<<grid, 32 * warps, smem, st>>>(census, d, view_mask, wtaL, wtaR);
     lc.add();
 }
 
