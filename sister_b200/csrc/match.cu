@@ -190,11 +190,39 @@ __device__ __forceinline__ int median9(int v0, int v1, int v2, int v3, int v4, i
     return v4;
 }
 
+// packed s16x2 compare-exchange: two pixels per register
+__device__ __forceinline__ void sort2p(uint32_t &a, uint32_t &b)
+{
+    const uint32_t lo = __vmins2(a, b), hi = __vmaxs2(a, b);
+    a = lo; b = hi;
+}
+// the 19-exchange network of postprocess.cpp:52-58 on two pixels at once
+__device__ __forceinline__ uint32_t median9p(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t v4, uint32_t v5, uint32_t v6,
+                                             uint32_t v7, uint32_t v8)
+{
+    sort2p(v1, v2); sort2p(v4, v5); sort2p(v7, v8);
+    sort2p(v0, v1); sort2p(v3, v4); sort2p(v6, v7);
+    sort2p(v1, v2); sort2p(v4, v5); sort2p(v7, v8);
+    sort2p(v0, v3); sort2p(v5, v8); sort2p(v4, v7);
+    sort2p(v3, v6); sort2p(v1, v4); sort2p(v2, v5);
+    sort2p(v4, v7); sort2p(v4, v2); sort2p(v6, v4);
+    sort2p(v4, v2);
+    return v4;
+}
+
 // One block per map (8 maps: L and R of 4 views). Flat-array recursion (see oracle/sister_oracle.c
 // so_median_inplace): out[p] = med9(out[p-w-1..p-w+1], raw[p-1..p+1], raw[p+w-1..p+w+1]) for
-// p in [w+1, N-w-5], out[w] = 0, everything else unchanged. A row depends on the finished row above, and its
-// last element on its own first element (flat wrap-around), hence the two phases per row.
-// grid 8, block 1024, dynamic smem 3 * wv int16
+// p in [w+1, N-w-5], out[w] = 0, everything else unchanged. A row depends on the finished row above and its last
+// element on its own first element (flat wrap-around), so the recurrence is one block barrier per row and the work
+// between two barriers has to be as short as possible:
+//   * a thread filters TWO adjacent pixels at once with packed s16x2 min/max (VIMNMX.S16x2);
+//   * the raw rows are streamed through a flat shared-memory ring (kMedRing rows, cp.async kMedAhead rows ahead) and
+//     the filtered rows through a flat ring of 4 rows, so that "previous element of column 0" and "next element of
+//     column w-1" are plain flat neighbours, exactly as in the reference's flat pointer walk;
+//   * one thread does the first pair and then the last pair of the row (which needs the row's first output).
+// grid 8, block 1024, dynamic smem (kMedRing + 4) * wv int16
+constexpr int kMedRing = 8, kMedAhead = 6;
+
 __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wtaL, const int16_t *__restrict__ wtaR, Dims d,
                                                  unsigned view_mask, int16_t *__restrict__ medL, int16_t *__restrict__ medR)
 {
@@ -204,38 +232,97 @@ __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wta
     const int hv = view_rows(d, v), wv = view_cols(d, v);
     const int16_t *raw = ((m & 1) ? wtaR : wtaL) + (size_t)v * d.px;
     int16_t *out = ((m & 1) ? medR : medL) + (size_t)v * d.px;
-    int16_t *rows = reinterpret_cast<int16_t *>(smem_raw); // 3 rotating rows of filtered output
+    int16_t *ring = reinterpret_cast<int16_t *>(smem_raw);  // raw rows, flat, modulo kMedRing * wv
+    int16_t *filt = ring + (size_t)kMedRing * wv;           // filtered rows, flat, modulo 4 * wv
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    const int RS = kMedRing * wv, FS = 4 * wv;
     const long long N = (long long)hv * wv;
     const long long p_lo = wv + 1, p_hi = N - wv - 5;
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int c = tid; c < wv; c += nt) { int16_t x = raw[c]; rows[c] = x; out[c] = x; }
+    const int chunks = wv >> 2; // 8-byte chunks per row (wv % 4 == 0, postprocess.cpp:18)
+    auto stage = [&](int row) {
+        if (row < hv) {
+            const int16_t *src = raw + (size_t)row * wv;
+            const unsigned dst = ring_s + 2u * (unsigned)((row % kMedRing) * wv);
+            for (int c = tid; c < chunks; c += nt)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + 8u * c), "l"(src + 4 * c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    for (int row = 0; row < kMedAhead; row++) stage(row);
+    // row 0 is copied unchanged
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kMedAhead - 1) : "memory");
     __syncthreads();
+    for (int c = tid; c < wv; c += nt) { const int16_t x = ring[c]; filt[c] = x; out[c] = x; }
+    const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(ring);
+    const uint32_t *filt32 = reinterpret_cast<const uint32_t *>(filt);
     for (int r = 1; r < hv; r++) {
-        int16_t *cur = rows + (size_t)(r % 3) * wv;
-        const int16_t *prev = rows + (size_t)((r + 2) % 3) * wv;  // row r-1
-        const int16_t *prev2 = rows + (size_t)((r + 1) % 3) * wv; // row r-2 (valid for r >= 2)
+        // rows <= r + 2 must have landed: rows 0 .. kMedAhead + r - 2 are committed
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(kMedAhead - 4) : "memory");
+        __syncthreads(); // publishes the raw rows and the filtered row r - 1; everyone is done with row r - 1
+        stage(kMedAhead + r - 1);
         const long long base = (long long)r * wv;
-        for (int c = tid; c < wv; c += nt) {
-            const long long p = base + c;
-            int val;
-            if (p == wv) val = 0; // the zero-initialised lastMedian lands here (postprocess.cpp:29,61-63)
-            else if (p < p_lo || p > p_hi) val = raw[p];
-            else if (c == wv - 1) continue; // phase 2
-            else {
-                int a0 = (c == 0) ? prev2[wv - 1] : prev[c - 1];
-                val = median9(a0, prev[c], prev[c + 1], raw[p - 1], raw[p], raw[p + 1], raw[p + wv - 1], raw[p + wv], raw[p + wv + 1]);
+        const int fprev = ((r - 1) & 3) * wv, fcur = (r & 3) * wv; // flat ring index of column 0 of rows r-1, r
+        const int rb = (r % kMedRing) * wv;                         // raw ring index of (r, 0)
+        const int rb1 = ((r + 1) % kMedRing) * wv;                  // raw ring index of (r+1, 0)
+        const bool plain_row = r >= 2 && r <= hv - 3;               // no position of this row is special
+        // ---- interior pairs (c, c+1), c even in [2, wv-4]: all nine neighbours lie inside the rows' own slots ----
+        for (int c = 2 + 2 * tid; c <= wv - 4; c += 2 * nt) {
+            const int h = c >> 1;
+            const uint32_t pa = filt32[(fprev >> 1) + h - 1], pb = filt32[(fprev >> 1) + h], pc = filt32[(fprev >> 1) + h + 1];
+            const uint32_t qa = ring32[(rb >> 1) + h - 1], qb = ring32[(rb >> 1) + h], qc = ring32[(rb >> 1) + h + 1];
+            const uint32_t sa = ring32[(rb1 >> 1) + h - 1], sb = ring32[(rb1 >> 1) + h], sc = ring32[(rb1 >> 1) + h + 1];
+            uint32_t val;
+            if (r < hv - 1)
+                val = median9p(__byte_perm(pa, pb, 0x5432), pb, __byte_perm(pb, pc, 0x5432), __byte_perm(qa, qb, 0x5432), qb,
+                               __byte_perm(qb, qc, 0x5432), __byte_perm(sa, sb, 0x5432), sb, __byte_perm(sb, sc, 0x5432));
+            else
+                val = qb;
+            if (!plain_row) { // per-pixel exceptions: p < p_lo or p > p_hi keep the raw value
+                const long long p = base + c;
+                if (p < p_lo || p > p_hi) val = (val & 0xFFFF0000u) | (qb & 0xFFFFu);
+                if (p + 1 < p_lo || p + 1 > p_hi) val = (val & 0xFFFFu) | (qb & 0xFFFF0000u);
             }
-            cur[c] = (int16_t)val;
+            reinterpret_cast<uint32_t *>(filt)[(fcur >> 1) + h] = val;
+            *reinterpret_cast<uint32_t *>(out + base + c) = val;
         }
-        __syncthreads();
-        if (tid == 0) {
-            const long long p = base + wv - 1;
-            if (p >= p_lo && p <= p_hi && p != wv)
-                cur[wv - 1] = (int16_t)median9(prev[wv - 2], prev[wv - 1], cur[0], raw[p - 1], raw[p], raw[p + 1], raw[p + wv - 1], raw[p + wv], raw[p + wv + 1]);
+        // ---- the two border pairs, literal (flat neighbours wrap through the rings): lanes 0..3 of the last warp take
+        // columns 0, 1, w-2, w-1. Column w-1 needs this row's column-0 output as ONE of its nine inputs: the median of
+        // nine with one unknown x is clamp(x, k3, k4) with k3, k4 the 4th and 5th smallest of the other eight, and
+        // those are the network's outputs for x = -inf and x = +inf -- evaluated together as the two packed halves, in
+        // parallel with column 0, so the row's critical path is one network, not two. ----
+        if (tid >= nt - 32) {
+            const int lane = tid & 31;
+            auto F = [&](int idx) -> int { if (idx < 0) idx += FS; if (idx >= FS) idx -= FS; return filt[idx]; };
+            auto R = [&](int idx) -> int { if (idx < 0) idx += RS; if (idx >= RS) idx -= RS; return ring[idx]; };
+            auto dup = [](int x) -> uint32_t { return ((uint32_t)x & 0xFFFFu) * 0x10001u; };
+            const int c = lane == 0 ? 0 : lane == 1 ? 1 : lane == 2 ? wv - 2 : wv - 1;
+            const long long p = base + c;
+            const bool is_median = lane < 4 && p != wv && p >= p_lo && p <= p_hi;
+            uint32_t packed = 0;
+            int val = 0;
+            if (lane < 4) {
+                if (is_median) {
+                    const uint32_t a2 = (lane == 3) ? 0x7FFF8000u /* (lo: -32768, hi: +32767) */ : dup(F(fprev + c + 1));
+                    packed = median9p(dup(F(fprev + c - 1)), dup(F(fprev + c)), a2, dup(R(rb + c - 1)), dup(R(rb + c)), dup(R(rb + c + 1)),
+                                      dup(R(rb + c + wv - 1)), dup(R(rb + c + wv)), dup(R(rb + c + wv + 1)));
+                    val = (int)(int16_t)(packed & 0xFFFFu);
+                } else if (p != wv) {
+                    val = R(rb + c); // p < p_lo or p > p_hi keeps the raw value; p == w is the zero of postprocess.cpp:29,61-63
+                }
+            }
+            const int first = __shfl_sync(0xFFFFFFFFu, val, 0); // this row's column-0 output
+            if (lane == 3 && is_median) {
+                const int k3 = (int)(int16_t)(packed & 0xFFFFu), k4 = (int)(int16_t)(packed >> 16);
+                val = min(max(first, k3), k4);
+            }
+            if (lane < 4) {
+                filt[fcur + c] = (int16_t)val;
+                out[base + c] = (int16_t)val;
+            }
         }
-        __syncthreads();
-        for (int c = tid; c < wv; c += nt) out[base + c] = cur[c];
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
 // grid (ceil(wv/256), max(hv), 4), block 256
@@ -270,7 +357,7 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
         cudaFuncSetAttribute(k_median, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
-    k_median<<<8, 1024, (size_t)3 * m * sizeof(int16_t), st>>>(wtaL, wtaR, d, view_mask, medL, medR);
+    k_median<<<8, 1024, (size_t)(kMedRing + 4) * m * sizeof(int16_t), st>>>(wtaL, wtaR, d, view_mask, medL, medR);
     lc.add();
     dim3 grid((m + 255) / 256, m, 4);
     k_lrc_mask<<<grid, 256, 0, st>>>(medL, medR, d, view_mask, lr_final, masks);
