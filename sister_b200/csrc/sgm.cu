@@ -34,8 +34,12 @@ namespace sister {
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint32_t kP1x2 = (uint32_t)kP1 * 0x10001u;
 constexpr uint32_t kP2x2 = (uint32_t)kP2 * 0x10001u;
-constexpr int kRing = 12;         // steps of fused cost in flight per warp
-constexpr int kChainWarps = 8;    // warps (= chains) per block
+constexpr int kRing = 12;         // steps of fused cost in flight per chain
+constexpr int kChainWarps = 8;    // warps per block
+
+// Lane mapping. A chain occupies LPC lanes of a warp (LPC = 16 for D <= 256: two chains per warp, so the per-step
+// fixed work -- shuffles, border selects, the min reduction, loop and cursor arithmetic -- is paid once for two
+// chains; LPC = 32 above). Lane sl of a chain owns the 2 * NR consecutive disparities sl * 2NR ..., two per register.
 
 // ---------------------------------------------------------------------------------------------- small helpers
 
@@ -43,84 +47,102 @@ __device__ __forceinline__ void cp_async8(unsigned smem_dst, const void *gmem_sr
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// number of valid packed registers of this lane (disparities lane*2NR + 2k, +1 are valid for k < nvalid)
-template <int NR> __device__ __forceinline__ int lane_nvalid(int D, int lane)
+// number of valid packed registers of this lane (disparities sl*2NR + 2k, +1 are valid for k < nvalid)
+template <int NR> __device__ __forceinline__ int lane_nvalid(int D, int sl)
 {
-    int n = D / 2 - lane * NR;
+    int n = D / 2 - sl * NR;
     return n < 0 ? 0 : (n > NR ? NR : n);
 }
 
-__device__ __forceinline__ unsigned warp_min_s16x2(uint32_t m2)
+// min over the chain's lanes of both halves of m2, returned in both halves: (m, m). All values are in [0, 0x3FFF], so
+// with equal halves the unsigned 32-bit order is the 16-bit order and one CREDUX.MIN per chain does it.
+template <int LPC> __device__ __forceinline__ uint32_t chain_min2(uint32_t m2, int sub)
 {
-    unsigned m = min(m2 & 0xFFFFu, m2 >> 16);
-    return __reduce_min_sync(kFull, m);
+    const uint32_t v = __vmins2(m2, __byte_perm(m2, m2, 0x1032));
+    if constexpr (LPC == 32) {
+        return __reduce_min_sync(kFull, v);
+    } else {
+        const uint32_t lo = __reduce_min_sync(kFull, sub == 0 ? v : 0x7FFF7FFFu);
+        const uint32_t hi = __reduce_min_sync(kFull, sub == 0 ? 0x7FFF7FFFu : v);
+        return sub == 0 ? lo : hi;
+    }
 }
 
 // Neighbour registers of a packed state vector: E[k] = (d-1 of the low half, low half), E[k+1] = (high half, d+1 of
-// the high half). The two values that live in the adjacent lanes come by shuffle; the outermost ones are kInf2.
-template <int NR> __device__ __forceinline__ void neighbours(const uint32_t (&a)[NR], int lane, uint32_t (&E)[NR + 1])
+// the high half). The two values that live in the adjacent lanes come by shuffle; at the chain's first / last lane
+// they are kInf2 (L(-1) = L(D) = 65535 in the reference, sgm.cpp:84-87).
+template <int NR> __device__ __forceinline__ void neighbours(const uint32_t (&a)[NR], bool first_lane, bool last_lane, uint32_t (&E)[NR + 1])
 {
     uint32_t up = __shfl_up_sync(kFull, a[NR - 1], 1);
     uint32_t dn = __shfl_down_sync(kFull, a[0], 1);
-    if (lane == 0) up = kInf2;
-    if (lane == 31) dn = kInf2;
+    if (first_lane) up = kInf2;
+    if (last_lane) dn = kInf2;
     E[0] = __byte_perm(up, a[0], 0x5432);
 #pragma unroll
     for (int k = 1; k < NR; k++) E[k] = __byte_perm(a[k - 1], a[k], 0x5432);
     E[NR] = __byte_perm(a[NR - 1], dn, 0x5432);
 }
 
+struct LaneInfo {
+    int sl, sub, nvalid;
+    bool first_lane, last_lane;
+};
+
 // One SGM step of one chain: a = clamped normalised state of the predecessor (pad registers = kInf2).
 // Writes q = L' - C (in [0, P2]) and the new state.
-template <int NR, bool FULL>
-__device__ __forceinline__ void chain_step(uint32_t (&a)[NR], const uint32_t (&c)[NR], int lane, int nvalid, uint32_t (&q)[NR])
+template <int NR, int LPC, bool FULL>
+__device__ __forceinline__ void chain_step(uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo &li, uint32_t (&q)[NR])
 {
     uint32_t E[NR + 1], L[NR];
-    neighbours<NR>(a, lane, E);
+    neighbours<NR>(a, li.first_lane, li.last_lane, E);
     uint32_t m2 = kInf2;
 #pragma unroll
     for (int k = 0; k < NR; k++) {
         const uint32_t x = __viaddmin_s16x2(E[k], kP1x2, a[k]);
         q[k] = __viaddmin_s16x2(E[k + 1], kP1x2, x);
         L[k] = q[k] + c[k];
-        if (FULL || k < nvalid) m2 = __vmins2(m2, L[k]);
+        if (FULL || k < li.nvalid) m2 = __vmins2(m2, L[k]);
     }
-    const unsigned m = warp_min_s16x2(m2);
-    const uint32_t neg = ((0u - m) & 0xFFFFu) * 0x10001u; // (-m, -m) as packed s16
+    const uint32_t mm = chain_min2<LPC>(m2, li.sub);
+    const uint32_t cap = mm + kP2x2;
 #pragma unroll
     for (int k = 0; k < NR; k++) {
-        const uint32_t n = __viaddmin_s16x2(L[k], neg, kP2x2); // min(L - m, P2)
-        a[k] = (FULL || k < nvalid) ? n : kInf2;
+        const uint32_t n = __vmins2(L[k], cap) - mm; // min(L - m, P2); L >= m in both halves, no borrow
+        a[k] = (FULL || k < li.nvalid) ? n : kInf2;
     }
 }
 
 // The first cell of a column / diagonal chain lies on the first line of the pass: L = C (sgm.cpp:103-138).
-template <int NR, bool FULL>
-__device__ __forceinline__ void chain_first_cell(uint32_t (&a)[NR], const uint32_t (&c)[NR], int nvalid, uint32_t (&q)[NR])
+template <int NR, int LPC, bool FULL>
+__device__ __forceinline__ void chain_first_cell(uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo &li, uint32_t (&q)[NR])
 {
     uint32_t m2 = kInf2;
 #pragma unroll
     for (int k = 0; k < NR; k++) {
         q[k] = 0u;
-        if (FULL || k < nvalid) m2 = __vmins2(m2, c[k]);
+        if (FULL || k < li.nvalid) m2 = __vmins2(m2, c[k]);
     }
-    const unsigned m = warp_min_s16x2(m2);
-    const uint32_t neg = ((0u - m) & 0xFFFFu) * 0x10001u;
+    const uint32_t mm = chain_min2<LPC>(m2, li.sub);
+    const uint32_t cap = mm + kP2x2;
 #pragma unroll
     for (int k = 0; k < NR; k++) {
-        const uint32_t n = __viaddmin_s16x2(c[k], neg, kP2x2);
-        a[k] = (FULL || k < nvalid) ? n : kInf2;
+        const uint32_t n = __vmins2(c[k], cap) - mm;
+        a[k] = (FULL || k < li.nvalid) ? n : kInf2;
     }
 }
 
 // The horizontal path on the first line of a pass (sgm.cpp:141-190): plain int arithmetic on the un-normalised
 // values, then saturate_cast<uint16>(uint8) truncation (types.h:28). The state carried along the line is the truncated
-// value Lq and its minimum m; the byte written to the path volume is the truncated value itself.
-template <int NR, bool FULL>
-__device__ __forceinline__ void first_line_step(uint32_t (&Lq)[NR], unsigned &m, const uint32_t (&c)[NR], int lane, int nvalid,
+// value Lq and its minimum (mm, both halves); the byte written to the path volume is the truncated value itself.
+template <int NR, int LPC, bool FULL>
+__device__ __forceinline__ void first_line_step(uint32_t (&Lq)[NR], uint32_t &mm, const uint32_t (&c)[NR], const LaneInfo &li,
                                                 bool first_column, uint32_t (&q)[NR])
 {
     if (first_column) {
@@ -128,8 +150,8 @@ __device__ __forceinline__ void first_line_step(uint32_t (&Lq)[NR], unsigned &m,
         for (int k = 0; k < NR; k++) q[k] = c[k];
     } else {
         uint32_t E[NR + 1];
-        neighbours<NR>(Lq, lane, E);
-        const uint32_t mm = m * 0x10001u, p2 = mm + kP2x2;
+        neighbours<NR>(Lq, li.first_lane, li.last_lane, E);
+        const uint32_t p2 = mm + kP2x2;
 #pragma unroll
         for (int k = 0; k < NR; k++) {
             const uint32_t x = __viaddmin_s16x2(E[k], kP1x2, Lq[k]);
@@ -140,10 +162,10 @@ __device__ __forceinline__ void first_line_step(uint32_t (&Lq)[NR], unsigned &m,
     uint32_t m2 = kInf2;
 #pragma unroll
     for (int k = 0; k < NR; k++) {
-        Lq[k] = (FULL || k < nvalid) ? q[k] : kInf2;
+        Lq[k] = (FULL || k < li.nvalid) ? q[k] : kInf2;
         m2 = __vmins2(m2, Lq[k]);
     }
-    m = warp_min_s16x2(m2);
+    mm = chain_min2<LPC>(m2, li.sub);
 }
 
 // ---------------------------------------------------------------------------------------------- chain geometry
@@ -152,39 +174,63 @@ struct Chain {
     int i, j;       // first cell
     int si, sj;     // step
     int enter;      // column a diagonal chain re-enters at after leaving the frame
-    int nsteps;
     int vol;        // path volume index: 4 * pass + path
-    int kind;       // 0: r0 on an ordinary row (a = 0), 1: r0 on the first line, 2: column / diagonal chain
 };
 
-// Chain numbering: [2 first-line r0 chains][2 * (Hp-1) row chains][2 * 3 * Wp column and diagonal chains]
-__host__ __device__ inline long long chain_count(const Dims &d) { return 2 + 2LL * (d.Hp - 1) + 6LL * d.Wp; }
-
-__device__ __forceinline__ bool chain_decode(const Dims &d, long long g, Chain &ch)
+// Chain numbering, four sections, each padded to a multiple of `cpw` (chains per warp) so that a warp never mixes
+// kinds; a padding slot repeats the section's last chain (it recomputes and rewrites the same bytes):
+//   kind 1  [2]              r0 on the first line of pass 0 / pass 1
+//   kind 0  [2 * (Hp-1)]     r0 on the other rows
+//   kind 2  [2 * Wp]         r2 columns
+//   kind 3  [4 * Wp]         r1 / r3 wrapped diagonals
+struct Sections {
+    long long n[4], o[5];
+};
+__host__ __device__ inline Sections chain_sections(const Dims &d, int cpw)
 {
-    if (g >= chain_count(d)) return false;
-    if (g < 2) {
-        const int p = (int)g;
+    Sections s;
+    const long long cnt[4] = {2, 2LL * (d.Hp - 1), 2LL * d.Wp, 4LL * d.Wp};
+    s.o[0] = 0;
+    for (int k = 0; k < 4; k++) {
+        s.n[k] = cnt[k];
+        s.o[k + 1] = s.o[k] + (cnt[k] + cpw - 1) / cpw * cpw;
+    }
+    return s;
+}
+
+// returns the kind (0..3) or -1 when g is past the end
+__device__ __forceinline__ int chain_decode(const Dims &d, const Sections &sec, long long g, Chain &ch, int &nsteps)
+{
+    if (g >= sec.o[4]) return -1;
+    if (g < sec.o[1]) {
+        const int p = (int)min(g, sec.n[0] - 1);
         ch.i = p ? d.Hp - 1 : 0; ch.j = p ? d.Wp - 1 : 0; ch.si = 0; ch.sj = p ? -1 : 1; ch.enter = 0;
-        ch.nsteps = d.Wp; ch.vol = 4 * p; ch.kind = 1;
-        return true;
+        ch.vol = 4 * p; nsteps = d.Wp;
+        return 1;
     }
-    g -= 2;
-    if (g < 2LL * (d.Hp - 1)) {
-        const int p = (int)(g / (d.Hp - 1)), r = (int)(g % (d.Hp - 1));
+    if (g < sec.o[2]) {
+        const long long idx = min(g - sec.o[1], sec.n[1] - 1);
+        const int p = (int)(idx / (d.Hp - 1)), r = (int)(idx % (d.Hp - 1));
         ch.i = p ? r : r + 1; ch.j = p ? d.Wp - 1 : 0; ch.si = 0; ch.sj = p ? -1 : 1; ch.enter = 0;
-        ch.nsteps = d.Wp; ch.vol = 4 * p; ch.kind = 0;
-        return true;
+        ch.vol = 4 * p; nsteps = d.Wp;
+        return 0;
     }
-    g -= 2LL * (d.Hp - 1);
-    const int p = (int)(g / (3LL * d.Wp));
-    const int rem = (int)(g % (3LL * d.Wp)), col = rem / 3, type = rem % 3; // type 0: r1, 1: r2, 2: r3
+    if (g < sec.o[3]) {
+        const long long idx = min(g - sec.o[2], sec.n[2] - 1);
+        const int p = (int)(idx / d.Wp), col = (int)(idx % d.Wp);
+        ch.i = p ? d.Hp - 1 : 0; ch.j = col; ch.si = p ? -1 : 1; ch.sj = 0; ch.enter = 0;
+        ch.vol = 4 * p + 2; nsteps = d.Hp;
+        return 2;
+    }
+    const long long idx = min(g - sec.o[3], sec.n[3] - 1);
+    const int p = (int)(idx / (2LL * d.Wp));
+    const int rem = (int)(idx % (2LL * d.Wp)), col = rem >> 1, r3 = rem & 1;
     const int dj = p ? -1 : 1, j1 = p ? d.Wp - 1 : 0, jl = p ? 0 : d.Wp - 1;
     ch.i = p ? d.Hp - 1 : 0; ch.j = col; ch.si = dj;
-    ch.sj = type == 0 ? dj : type == 1 ? 0 : -dj;
-    ch.enter = type == 0 ? j1 : jl;
-    ch.nsteps = d.Hp; ch.vol = 4 * p + 1 + type; ch.kind = 2;
-    return true;
+    ch.sj = r3 ? -dj : dj;
+    ch.enter = r3 ? jl : j1;
+    ch.vol = 4 * p + (r3 ? 3 : 1); nsteps = d.Hp;
+    return 3;
 }
 
 // ---------------------------------------------------------------------------------------------- the path kernel
@@ -193,7 +239,7 @@ __device__ __forceinline__ bool chain_decode(const Dims &d, long long g, Chain &
 template <int NR, bool FULL> __device__ __forceinline__ void store_q(uint8_t *dst, const uint32_t (&q)[NR], int nvalid)
 {
     if constexpr (NR % 2 == 0) {
-        // lane * 2NR is a multiple of 4 and cell * D a multiple of 8: 32-bit stores are always aligned
+        // sl * 2NR is a multiple of 4 and cell * D a multiple of 8: 32-bit stores are always aligned
         if (FULL || nvalid == NR) {
             uint32_t w[NR / 2];
 #pragma unroll
@@ -216,36 +262,57 @@ template <int NR, bool FULL> __device__ __forceinline__ void store_q(uint8_t *ds
     }
 }
 
-// Per-warp view of one chain: cursors are 32-bit offsets in units of 8 bytes (D % 8 == 0) from the volume base, turned
-// into addresses with one IMAD.WIDE; the cost ring is kRing slots of 64 * NR bytes.
-template <int NR, bool FULL> struct ChainRun {
-    static constexpr int kSlotBytes = 64 * NR;
+// Per-lane view of one chain: cursors are 32-bit offsets in units of 8 bytes (D % 8 == 0) from the volume base, turned
+// into addresses with one IMAD.WIDE; the cost ring is kRing slots of LPC * 2NR bytes per chain.
+template <int NR, int LPC, bool FULL> struct ChainRun {
+    static constexpr int kSlotBytes = LPC * 2 * NR;
     static constexpr unsigned kRingBytes = kRing * kSlotBytes;
-    const uint8_t *fused_lane; // fused + lane * 8
-    uint8_t *q_lane;           // path volume + lane * 2NR
-    unsigned ring_ld;          // shared address of the ring + lane * 2NR (reads)
-    unsigned ring_st;          // shared address of the ring + lane * 8   (cp.async destination)
-    int lane, nvalid;
-    bool ld0, ld1;
+    // the two chains of a warp read their rings in the same instruction: offset the second ring by 16 banks
+    static constexpr unsigned kChainPitch = kRingBytes + ((kRingBytes % 128 == 0 && LPC < 32) ? 64 : 0);
+    static constexpr int kRounds = (NR + 3) / 4;    // 8-byte cp.async rounds: LPC lanes fetch LPC * 8 bytes per round
+    static constexpr int kRounds16 = (NR + 7) / 8;  // 16-byte rounds (D % 16 == 0)
+    const uint8_t *fused_lane; // fused + sl * 8 (or sl * 16)
+    uint8_t *q_lane;           // path volume + sl * 2NR
+    unsigned ring_ld;          // shared address of the chain's ring + sl * 2NR (reads)
+    unsigned ring_st;          // shared address of the chain's ring + sl * 8 (or sl * 16): cp.async destination
+    int D, sl;
+    bool wide;                 // D % 16 == 0: 16-byte copies
     unsigned rd_off = 0;                           // ring slot of the step being consumed
     unsigned wr_off = (kRing - 1) * kSlotBytes;    // free slot: the one consumed in the previous step
 
     __device__ __forceinline__ void issue(unsigned slot_off, int off8) const
     {
         const uint8_t *src = fused_lane + (long long)off8 * 8;
-        if (ld0) cp_async8(ring_st + slot_off, src);
-        if (NR > 4 && ld1) cp_async8(ring_st + slot_off + 256, src + 256);
+        if (wide) {
+#pragma unroll
+            for (int r = 0; r < kRounds16; r++)
+                if ((sl + r * LPC) * 16 < D) cp_async16(ring_st + slot_off + r * LPC * 16, src + r * LPC * 16);
+        } else {
+#pragma unroll
+            for (int r = 0; r < kRounds; r++)
+                if ((sl + r * LPC) * 8 < D) cp_async8(ring_st + slot_off + r * LPC * 8, src + r * LPC * 8);
+        }
     }
     __device__ __forceinline__ void consume(uint32_t (&c)[NR]) const
     {
         cp_async_wait<kRing - 2>();
         __syncwarp();
         const unsigned src = ring_ld + rd_off;
+        if constexpr (NR % 2 == 0) {
 #pragma unroll
-        for (int k = 0; k < NR; k++) {
-            unsigned short v;
-            asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(src + 2 * k) : "memory");
-            c[k] = __byte_perm((uint32_t)v, 0u, 0x4140);
+            for (int k = 0; k < NR / 2; k++) {
+                uint32_t v;
+                asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(src + 4 * k) : "memory");
+                c[2 * k] = __byte_perm(v, 0u, 0x4140);
+                c[2 * k + 1] = __byte_perm(v, 0u, 0x4342);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NR; k++) {
+                unsigned short v;
+                asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(src + 2 * k) : "memory");
+                c[k] = __byte_perm((uint32_t)v, 0u, 0x4140);
+            }
         }
     }
     // returns the free slot (consumed one step ago, every lane is past its reads: a __syncwarp lies in between),
@@ -259,52 +326,61 @@ template <int NR, bool FULL> struct ChainRun {
     }
 };
 
-// grid ceil(chain_count / kChainWarps), block kChainWarps * 32, dynamic smem kChainWarps * kRing * 64 * NR bytes
-template <int NR, bool FULL>
+// grid ceil(chains / (kChainWarps * 32 / LPC)), block kChainWarps * 32, dynamic smem kChainWarps * kRing * 64 * NR bytes
+template <int NR, int LPC, bool FULL>
 __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, uint8_t *__restrict__ qvol)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CPW = 32 / LPC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    LaneInfo li;
+    li.sl = lane % LPC;
+    li.sub = lane / LPC;
+    li.first_lane = li.sl == 0;
+    li.last_lane = li.sl == LPC - 1;
+    const Sections sec = chain_sections(d, CPW);
     Chain ch;
-    if (!chain_decode(d, (long long)blockIdx.x * kChainWarps + warp, ch)) return;
+    int nsteps = 0;
+    const int kind = chain_decode(d, sec, ((long long)blockIdx.x * kChainWarps + warp) * CPW + li.sub, ch, nsteps);
+    if (kind < 0) return; // warp-uniform: sections are padded to whole warps
     const int D = d.D, Wp = d.Wp;
-    using Run = ChainRun<NR, FULL>;
+    using Run = ChainRun<NR, LPC, FULL>;
     Run run;
-    run.lane = lane;
-    run.nvalid = FULL ? NR : lane_nvalid<NR>(D, lane);
-    run.ld0 = lane * 8 < D;
-    run.ld1 = lane * 8 + 256 < D;
-    run.fused_lane = fused + lane * 8;
-    run.q_lane = qvol + (size_t)ch.vol * (size_t)d.cells + lane * 2 * NR;
+    run.D = D;
+    run.sl = li.sl;
+    li.nvalid = FULL ? NR : lane_nvalid<NR>(D, li.sl);
+    run.wide = (D & 15) == 0;
+    run.fused_lane = fused + li.sl * (run.wide ? 16 : 8);
+    run.q_lane = qvol + (size_t)ch.vol * (size_t)d.cells + li.sl * 2 * NR;
     {
-        const unsigned base = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)warp * Run::kRingBytes);
-        run.ring_ld = base + lane * 2 * NR;
-        run.ring_st = base + lane * 8;
+        const unsigned base = (unsigned)__cvta_generic_to_shared(smem_raw + ((size_t)warp * CPW + li.sub) * Run::kChainPitch);
+        run.ring_ld = base + li.sl * 2 * NR;
+        run.ring_st = base + li.sl * (run.wide ? 16 : 8);
     }
-    const int nvalid = run.nvalid;
+    const int nvalid = li.nvalid;
     const int D8 = D >> 3;
     // a chain advances by a constant offset; a diagonal chain that steps over a side border re-enters at the opposite
     // one (same row), a fixed correction of one row of cells
     const int stride8 = (ch.si * Wp + ch.sj) * D8;
     const int wrapfix8 = -ch.sj * Wp * D8;
     const int first8 = (ch.i * Wp + ch.j) * D8;
-    const int nsteps = ch.nsteps;
 
     // prologue: kRing - 1 steps in flight
     int poff = first8, pj = ch.j;
-    const bool diag = ch.kind == 2 && ch.sj != 0;
+    const bool diag = kind == 3;
 #pragma unroll 1
     for (int t = 0; t < kRing - 1; t++) {
-        run.issue(t * Run::kSlotBytes, poff); // nsteps >= 16 > kRing (check_shape)
+        run.issue(t * Run::kSlotBytes, poff); // nsteps >= 12 (check_shape, sister_test_sgm)
         cp_async_commit();
         poff += stride8;
         if (diag) { pj += ch.sj; if ((unsigned)pj >= (unsigned)Wp) { pj = ch.enter; poff += wrapfix8; } }
     }
 
     uint32_t a[NR], c[NR], q[NR];
-    if (ch.kind == 1) {
+    const int n_issue = nsteps - (kRing - 1);
+    if (kind == 1) {
         // ---- r0 on the first line of the pass: un-normalised, truncated state (sgm.cpp:141-190) ----
-        unsigned m = 0;
+        uint32_t mm = 0;
 #pragma unroll
         for (int k = 0; k < NR; k++) a[k] = kInf2;
         uint8_t *qlag = run.q_lane - (long long)(kRing - 1) * stride8 * 8;
@@ -312,9 +388,9 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
         for (int s = 0; s < nsteps; s++) {
             run.consume(c);
             const unsigned wr = run.advance_ring();
-            if (s < nsteps - (kRing - 1)) run.issue(wr, poff);
+            if (s < n_issue) run.issue(wr, poff);
             cp_async_commit();
-            first_line_step<NR, FULL>(a, m, c, lane, nvalid, s == 0, q);
+            first_line_step<NR, LPC, FULL>(a, mm, c, li, s == 0, q);
             store_q<NR, FULL>(qlag + (long long)poff * 8, q, nvalid);
             poff += stride8;
         }
@@ -323,12 +399,12 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
         // the store cursor is the prefetch cursor kRing - 1 steps ago: fold the lag into the base pointer
         uint8_t *qlag = run.q_lane - (long long)(kRing - 1) * stride8 * 8;
         int s = 0;
-        if (ch.kind == 2) {
+        if (kind == 2) {
             run.consume(c);
             const unsigned wr = run.advance_ring();
             run.issue(wr, poff);
             cp_async_commit();
-            chain_first_cell<NR, FULL>(a, c, nvalid, q);
+            chain_first_cell<NR, LPC, FULL>(a, c, li, q);
             store_q<NR, FULL>(qlag + (long long)poff * 8, q, nvalid);
             poff += stride8;
             s = 1;
@@ -336,14 +412,13 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
 #pragma unroll
             for (int k = 0; k < NR; k++) a[k] = (k < nvalid) ? 0u : kInf2;
         }
-        const int n_issue = nsteps - (kRing - 1);
 #pragma unroll 1
         for (; s < nsteps; s++) {
             run.consume(c);
             const unsigned wr = run.advance_ring();
             if (s < n_issue) run.issue(wr, poff);
             cp_async_commit();
-            chain_step<NR, FULL>(a, c, lane, nvalid, q);
+            chain_step<NR, LPC, FULL>(a, c, li, q);
             store_q<NR, FULL>(qlag + (long long)poff * 8, q, nvalid);
             poff += stride8;
         }
@@ -355,10 +430,9 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
             const unsigned wr = run.advance_ring();
             run.issue(wr, poff);
             cp_async_commit();
-            chain_first_cell<NR, FULL>(a, c, nvalid, q);
+            chain_first_cell<NR, LPC, FULL>(a, c, li, q);
             store_q<NR, FULL>(run.q_lane + (long long)qoff * 8, q, nvalid);
         }
-        const int n_issue = nsteps - (kRing - 1);
 #pragma unroll 1
         for (int s = 1; s < nsteps; s++) {
             poff += stride8; pj += ch.sj;
@@ -373,7 +447,7 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
             const unsigned wr = run.advance_ring();
             if (s < n_issue) run.issue(wr, poff);
             cp_async_commit();
-            chain_step<NR, FULL>(a, c, lane, nvalid, q);
+            chain_step<NR, LPC, FULL>(a, c, li, q);
             store_q<NR, FULL>(run.q_lane + (long long)qoff * 8, q, nvalid);
         }
     }
@@ -448,39 +522,48 @@ __global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ f
 
 // ---------------------------------------------------------------------------------------------- launch
 
-template <int NR, bool FULL>
+template <int NR, int LPC, bool FULL>
 static void launch_paths(const uint8_t *fused, const Dims &d, uint8_t *qvol, cudaStream_t st)
 {
-    const size_t smem = (size_t)kChainWarps * kRing * 64 * NR;
+    constexpr int CPW = 32 / LPC;
+    const size_t smem = (size_t)kChainWarps * CPW * ChainRun<NR, LPC, FULL>::kChainPitch;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_sgm_paths<NR, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_sgm_paths<NR, LPC, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
-    const long long n = chain_count(d);
-    k_sgm_paths<NR, FULL><<<(unsigned)((n + kChainWarps - 1) / kChainWarps), kChainWarps * 32, smem, st>>>(fused, d, qvol);
+    const long long n = chain_sections(d, CPW).o[4];
+    const long long per_block = (long long)kChainWarps * CPW;
+    k_sgm_paths<NR, LPC, FULL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, smem, st>>>(fused, d, qvol);
+}
+
+template <int LPC>
+static void launch_paths_lpc(const uint8_t *fused, const Dims &d, uint8_t *qvol, cudaStream_t st)
+{
+    const int nr = (d.D + 2 * LPC - 1) / (2 * LPC); // disparities per lane = 2 * NR, chosen so that D fits in LPC lanes
+    const bool full = d.D == 2 * LPC * nr;
+#define SISTER_PATHS_CASE(N)                                                                    \
+    case N:                                                                                     \
+        if (full) launch_paths<N, LPC, true>(fused, d, qvol, st);                               \
+        else launch_paths<N, LPC, false>(fused, d, qvol, st);                                   \
+        break;
+    switch (nr) {
+        SISTER_PATHS_CASE(1) SISTER_PATHS_CASE(2) SISTER_PATHS_CASE(3) SISTER_PATHS_CASE(4)
+        SISTER_PATHS_CASE(5) SISTER_PATHS_CASE(6) SISTER_PATHS_CASE(7)
+    default:
+        if (full) launch_paths<8, LPC, true>(fused, d, qvol, st);
+        else launch_paths<8, LPC, false>(fused, d, qvol, st);
+        break;
+    }
+#undef SISTER_PATHS_CASE
 }
 
 void launch_sgm(const uint8_t *fused, const Dims &d, uint8_t *qvol, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
                 int *status, cudaStream_t st, LaunchCounter &lc)
 {
     (void)status;
-    const int nr = (d.D + 63) / 64; // disparities per lane = 2 * NR, chosen so that D fits in 32 lanes
-    const bool full = d.D == 64 * nr;
-#define SISTER_PATHS_CASE(N)                                                                    \
-    case N:                                                                                     \
-        if (full) launch_paths<N, true>(fused, d, qvol, st);                                    \
-        else launch_paths<N, false>(fused, d, qvol, st);                                        \
-        break;
-    switch (nr) {
-        SISTER_PATHS_CASE(1) SISTER_PATHS_CASE(2) SISTER_PATHS_CASE(3) SISTER_PATHS_CASE(4)
-        SISTER_PATHS_CASE(5) SISTER_PATHS_CASE(6) SISTER_PATHS_CASE(7)
-    default:
-        if (full) launch_paths<8, true>(fused, d, qvol, st);
-        else launch_paths<8, false>(fused, d, qvol, st);
-        break;
-    }
-#undef SISTER_PATHS_CASE
+    if (d.D <= 256) launch_paths_lpc<16>(fused, d, qvol, st); // two chains per warp
+    else launch_paths_lpc<32>(fused, d, qvol, st);
     lc.add();
     const long long groups = (d.px + 3) / 4;
     long long blocks = (groups + 7) / 8;

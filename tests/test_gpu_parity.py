@@ -152,3 +152,46 @@ def test_full_size_properties():
         batch = eng.compute_batch([plane, plane, plane], D, mode_mask=1)
         for r in batch:
             assert (r[0] == a[0]).all()
+
+
+@pytest.mark.parametrize("w,h,D,seed,modes", [(64, 48, 384, 21, 1), (32, 16, 512, 22, 1), (40, 32, 264, 23, 7)])
+def test_large_disparity_ranges_against_oracle(oracle_lib, w, h, D, seed, modes):
+    """D beyond the reference's own limit (postprocess.cpp:193 overflows at D >= 272): the widened oracle is the check
+    (BASELINE.json configs[3]/[4] use D = 384 and 512)."""
+    import sister_b200
+    views = make_rig(w, h, D, seed=seed, kind="smooth", channels=1)
+    with sister_b200.Engine(w, h, D, n_slots=1) as eng:
+        outs, raw = eng.compute(views, D, mode_mask=modes, want_raw=True)
+    ref, ref_raw = oracle_lib.compute_disparities(views, D, mode_mask=modes, want_raw=True)  # scalar: ~1 minute in total
+    for m in range(3):
+        if not (modes >> m) & 1:
+            continue
+        assert (raw[m] == ref_raw[m]).all(), f"mode {m}: {(raw[m] != ref_raw[m]).sum()} padded pixels differ"
+        assert (outs[m] == ref[m]).all()
+
+
+@pytest.mark.parametrize("D", [128, 256, 512])
+def test_baseline_distance_sweep_shapes(D):
+    """BASELINE.json configs[4]: 1280x960 rigs at D = 128..512 (up to 2.3e9 cells, beyond int32 indexing): properties
+    that need no CPU oracle -- determinism, and a fronto-parallel plane at disparity D/3 is recovered."""
+    import sister_b200
+    plane = make_rig(1280, 960, D, seed=5, kind="plane", noise=0, channels=1)
+    with sister_b200.Engine(1280, 960, D, n_slots=1) as eng:
+        a = eng.compute(plane, D, mode_mask=1)[0]
+        b = eng.compute(plane, D, mode_mask=1)[0]
+    assert (a == b).all()
+    # the generator rounds D / 3 to the nearest pixel; disp * 255 saturates only from disp >= 258 (hpp:116-118)
+    assert (a[32:-32, 32:-32] // 255 == int(round(D / 3.0))).mean() > 0.9
+
+
+def test_config4_large_frame_single_gpu():
+    """BASELINE.json configs[3] shape: 4096x3072, D = 384 (7.2e9 cells, 64.6 GB of volumes) on one B200."""
+    import sister_b200
+    D = 384
+    plane = make_rig(4096, 3072, D, seed=9, kind="plane", noise=0, channels=1)
+    with sister_b200.Engine(4096, 3072, D, n_slots=1) as eng:
+        a = eng.compute(plane, D, mode_mask=1)[0]
+        b = eng.compute(plane, D, mode_mask=1)[0]
+    assert (a == b).all()
+    inner = a[64:-64, 64:-64] // 255
+    assert (inner == int(round(D / 3.0))).mean() > 0.9
