@@ -112,8 +112,8 @@ __device__ __forceinline__ void match_block(unsigned c1_s, unsigned c2_s, unsign
     }
 }
 
-// grid (max(hv), 4), block 32 * ceil(max(wv) / (32 K)) (at most 1024), dynamic smem: 2 * wv u64 + wv u32
-__global__ void __launch_bounds__(1024) k_match_wta(const unsigned long long *__restrict__ census, Dims d, unsigned view_mask,
+// grid (max(hv), 4), block 32 * min(ceil(max(wv) / (32 K)), 13), dynamic smem: 2 * wv u64 + wv u32; three blocks per SM
+__global__ void __launch_bounds__(416, 3) k_match_wta(const unsigned long long *__restrict__ census, Dims d, unsigned view_mask,
                                                     int16_t *__restrict__ wtaL, int16_t *__restrict__ wtaR)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -163,7 +163,7 @@ void launch_match_wta(const unsigned long long *census, const Dims &d, unsigned 
         attr_done = true;
     }
     int warps = (m + 32 * kMatchK - 1) / (32 * kMatchK);
-    if (warps > 32) warps = 32;
+    if (warps > 13) warps = 13;
     dim3 grid(m, 4);
     k_match_wta<<<grid, 32 * warps, smem, st>>>(census, d, view_mask, wtaL, wtaR);
     lc.add();
@@ -374,7 +374,7 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
 // Fast path (the only one the masks ever select, see the header comment): the view row is an ordinary census row and
 // the view column is >= D - 1, so every d has a partner and the cost is a plain popcount. Anything else takes the
 // literal per-cell formula of census.cpp:63-88,95-98 / hpp:264-276 below.
-// grid (ceil(Wp/T), ceil(Hp/T)), block 32 * T, dynamic smem 4 * T * (T + D) u64 + T * T bytes
+// grid (ceil(Wp/T), ceil(Hp/T)), block 32 * T, dynamic smem 4 * T * (T + D) u64 + 4 * T * T u64 + T * T bytes
 template <int T, int NK> // NK = D / 32 when D is a multiple of 32 (fully unrolled), 0 = any D
 __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__restrict__ census, const uint8_t *__restrict__ masks,
                                                  Dims d, unsigned view_mask, uint8_t *__restrict__ fused, int *__restrict__ status)
@@ -383,7 +383,8 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
     __shared__ unsigned s_any;
     unsigned long long *s = reinterpret_cast<unsigned long long *>(smem_raw);
     const int D = d.D, P = T + D; // line pitch (T + D - 1 used)
-    uint8_t *smask = smem_raw + (size_t)4 * T * P * 8;
+    unsigned long long *sc1 = s + (size_t)4 * T * P;        // the tile's own (centre) codes, per view: [v][li][lj]
+    uint8_t *smask = reinterpret_cast<uint8_t *>(sc1 + 4 * T * T);
     const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
     const int tid = threadIdx.x, nthr = 32 * T;
     if (tid == 0) s_any = 0;
@@ -423,6 +424,17 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
             const int col = col0 + x;
             sv[line * P + x] = (row_ok && col >= 0 && col < wv) ? __ldg(src + col) : 0ull;
         }
+        // the centre codes of the tile's pixels (row `line` of the tile)
+        if ((tid & 31) < T) {
+            const int i = i0 + line, j = j0 + (tid & 31);
+            unsigned long long c = 0;
+            if (i < d.Hp && j < d.Wp) {
+                int rv2, cc2;
+                image_to_view(d, v, i, j, rv2, cc2);
+                c = __ldg(census + (size_t)(2 * v) * d.px + (size_t)rv2 * wv + cc2);
+            }
+            sc1[(v * T + line) * T + (tid & 31)] = c;
+        }
     }
     __syncthreads();
     const int lane = tid & 31, li = tid >> 5;
@@ -447,7 +459,7 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
             image_to_view(d, v, i, j, rv, cc);
             const unsigned long long *line = s + (size_t)v * T * P + (size_t)((v < 2) ? li : lj) * P + (cc - cv_lo[v] + D - 1);
             if (rv >= 3 && rv < hv - 2 && cc >= D - 1) {
-                const unsigned long long c1 = __ldg(census + (size_t)(2 * v) * d.px + (size_t)rv * wv + cc);
+                const unsigned long long c1 = sc1[(v * T + li) * T + lj];
                 const unsigned c1lo = (unsigned)c1, c1hi = (unsigned)(c1 >> 32);
                 const unsigned long long *p = line - lane;
 #pragma unroll
@@ -462,7 +474,7 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
                 // (defined 0), d beyond the view column is 255 (census.cpp:76)
                 unsigned long long c1 = 0;
                 const bool popc_row = rv >= 3 && rv < hv - 2;
-                if (popc_row) c1 = __ldg(census + (size_t)(2 * v) * d.px + (size_t)rv * wv + cc);
+                if (popc_row) c1 = sc1[(v * T + li) * T + lj];
 #pragma unroll 1
                 for (int k = 0; k < NKC; k++) {
                     const int dd = lane + 32 * k;
@@ -492,7 +504,7 @@ template <int T, int NK>
 static void launch_fuse_t(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
                           int *status, cudaStream_t st)
 {
-    const size_t smem = (size_t)4 * T * (T + d.D) * 8 + T * T;
+    const size_t smem = (size_t)4 * T * (T + d.D) * 8 + (size_t)4 * T * T * 8 + T * T;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_fuse<T, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
