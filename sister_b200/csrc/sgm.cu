@@ -51,6 +51,12 @@ __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gmem_s
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
+// the same, issued only by lanes whose `on` register is non-zero (a register predicate keeps ptxas from
+// re-deriving the lane test from %tid in every step)
+__device__ __forceinline__ void cp_async16_if(unsigned smem_dst, const void *gmem_src, unsigned on)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n" ::"r"(smem_dst), "l"(gmem_src), "r"(on) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -63,45 +69,50 @@ template <int NR> __device__ __forceinline__ int lane_nvalid(int D, int sl)
 
 // min over the chain's lanes of both halves of m2, returned in both halves: (m, m). All values are in [0, 0x3FFF], so
 // with equal halves the unsigned 32-bit order is the 16-bit order and one CREDUX.MIN per chain does it.
-template <int LPC> __device__ __forceinline__ uint32_t chain_min2(uint32_t m2, int sub)
+template <int LPC> __device__ __forceinline__ uint32_t chain_min2(uint32_t m2, const uint32_t (&others)[32 / LPC])
 {
+    // others[g] = 0x7FFF7FFF when this lane is NOT in chain g of the warp, 0 when it is
     const uint32_t v = __vmins2(m2, __byte_perm(m2, m2, 0x1032));
     if constexpr (LPC == 32) {
         return __reduce_min_sync(kFull, v);
     } else {
-        const uint32_t lo = __reduce_min_sync(kFull, sub == 0 ? v : 0x7FFF7FFFu);
-        const uint32_t hi = __reduce_min_sync(kFull, sub == 0 ? 0x7FFF7FFFu : v);
-        return sub == 0 ? lo : hi;
+        uint32_t r = 0;
+#pragma unroll
+        for (int g = 0; g < 32 / LPC; g++) {
+            const uint32_t mg = __reduce_min_sync(kFull, v | others[g]); // lanes outside chain g contribute 0x7FFF7FFF
+            r |= mg & ~others[g];                                        // (x & ~0x7FFF7FFF) == 0 for x <= 0x3FFF3FFF
+        }
+        return r;
     }
 }
 
 // Neighbour registers of a packed state vector: E[k] = (d-1 of the low half, low half), E[k+1] = (high half, d+1 of
 // the high half). The two values that live in the adjacent lanes come by shuffle; at the chain's first / last lane
 // they are kInf2 (L(-1) = L(D) = 65535 in the reference, sgm.cpp:84-87).
-template <int NR> __device__ __forceinline__ void neighbours(const uint32_t (&a)[NR], bool first_lane, bool last_lane, uint32_t (&E)[NR + 1])
+template <int NR> __device__ __forceinline__ void neighbours(const uint32_t (&a)[NR], uint32_t up_mask, uint32_t dn_mask, uint32_t (&E)[NR + 1])
 {
-    uint32_t up = __shfl_up_sync(kFull, a[NR - 1], 1);
-    uint32_t dn = __shfl_down_sync(kFull, a[0], 1);
-    if (first_lane) up = kInf2;
-    if (last_lane) dn = kInf2;
+    // up_mask / dn_mask = kInf2 at the chain's first / last lane, 0 elsewhere: x | kInf2 >= kInf2 never wins a minimum
+    const uint32_t up = __shfl_up_sync(kFull, a[NR - 1], 1) | up_mask;
+    const uint32_t dn = __shfl_down_sync(kFull, a[0], 1) | dn_mask;
     E[0] = __byte_perm(up, a[0], 0x5432);
 #pragma unroll
     for (int k = 1; k < NR; k++) E[k] = __byte_perm(a[k - 1], a[k], 0x5432);
     E[NR] = __byte_perm(a[NR - 1], dn, 0x5432);
 }
 
-struct LaneInfo {
-    int sl, sub, nvalid;
-    bool first_lane, last_lane;
+template <int LPC> struct LaneInfo {
+    int sl, nvalid;
+    uint32_t up_mask, dn_mask;       // kInf2 at the chain's first / last lane
+    uint32_t others[32 / LPC];       // 0x7FFF7FFF for the chains of the warp this lane does not belong to
 };
 
 // One SGM step of one chain: a = clamped normalised state of the predecessor (pad registers = kInf2).
 // Writes q = L' - C (in [0, P2]) and the new state.
 template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ void chain_step(uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo &li, uint32_t (&q)[NR])
+__device__ __forceinline__ void chain_step(uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo<LPC> &li, uint32_t (&q)[NR])
 {
     uint32_t E[NR + 1], L[NR];
-    neighbours<NR>(a, li.first_lane, li.last_lane, E);
+    neighbours<NR>(a, li.up_mask, li.dn_mask, E);
     uint32_t m2 = kInf2;
 #pragma unroll
     for (int k = 0; k < NR; k++) {
@@ -110,7 +121,7 @@ __device__ __forceinline__ void chain_step(uint32_t (&a)[NR], const uint32_t (&c
         L[k] = q[k] + c[k];
         if (FULL || k < li.nvalid) m2 = __vmins2(m2, L[k]);
     }
-    const uint32_t mm = chain_min2<LPC>(m2, li.sub);
+    const uint32_t mm = chain_min2<LPC>(m2, li.others);
     const uint32_t cap = mm + kP2x2;
 #pragma unroll
     for (int k = 0; k < NR; k++) {
@@ -121,7 +132,7 @@ __device__ __forceinline__ void chain_step(uint32_t (&a)[NR], const uint32_t (&c
 
 // The first cell of a column / diagonal chain lies on the first line of the pass: L = C (sgm.cpp:103-138).
 template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ void chain_first_cell(uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo &li, uint32_t (&q)[NR])
+__device__ __forceinline__ void chain_first_cell(uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo<LPC> &li, uint32_t (&q)[NR])
 {
     uint32_t m2 = kInf2;
 #pragma unroll
@@ -129,7 +140,7 @@ __device__ __forceinline__ void chain_first_cell(uint32_t (&a)[NR], const uint32
         q[k] = 0u;
         if (FULL || k < li.nvalid) m2 = __vmins2(m2, c[k]);
     }
-    const uint32_t mm = chain_min2<LPC>(m2, li.sub);
+    const uint32_t mm = chain_min2<LPC>(m2, li.others);
     const uint32_t cap = mm + kP2x2;
 #pragma unroll
     for (int k = 0; k < NR; k++) {
@@ -142,7 +153,7 @@ __device__ __forceinline__ void chain_first_cell(uint32_t (&a)[NR], const uint32
 // values, then saturate_cast<uint16>(uint8) truncation (types.h:28). The state carried along the line is the truncated
 // value Lq and its minimum (mm, both halves); the byte written to the path volume is the truncated value itself.
 template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ void first_line_step(uint32_t (&Lq)[NR], uint32_t &mm, const uint32_t (&c)[NR], const LaneInfo &li,
+__device__ __forceinline__ void first_line_step(uint32_t (&Lq)[NR], uint32_t &mm, const uint32_t (&c)[NR], const LaneInfo<LPC> &li,
                                                 bool first_column, uint32_t (&q)[NR])
 {
     if (first_column) {
@@ -150,7 +161,7 @@ __device__ __forceinline__ void first_line_step(uint32_t (&Lq)[NR], uint32_t &mm
         for (int k = 0; k < NR; k++) q[k] = c[k];
     } else {
         uint32_t E[NR + 1];
-        neighbours<NR>(Lq, li.first_lane, li.last_lane, E);
+        neighbours<NR>(Lq, li.up_mask, li.dn_mask, E);
         const uint32_t p2 = mm + kP2x2;
 #pragma unroll
         for (int k = 0; k < NR; k++) {
@@ -165,7 +176,7 @@ __device__ __forceinline__ void first_line_step(uint32_t (&Lq)[NR], uint32_t &mm
         Lq[k] = (FULL || k < li.nvalid) ? q[k] : kInf2;
         m2 = __vmins2(m2, Lq[k]);
     }
-    mm = chain_min2<LPC>(m2, li.sub);
+    mm = chain_min2<LPC>(m2, li.others);
 }
 
 // ---------------------------------------------------------------------------------------------- chain geometry
@@ -239,14 +250,18 @@ __device__ __forceinline__ int chain_decode(const Dims &d, const Sections &sec, 
 template <int NR, bool FULL> __device__ __forceinline__ void store_q(uint8_t *dst, const uint32_t (&q)[NR], int nvalid)
 {
     if constexpr (NR % 2 == 0) {
-        // sl * 2NR is a multiple of 4 and cell * D a multiple of 8: 32-bit stores are always aligned
+        // sl * 2NR is a multiple of 4 (of 8 when NR % 4 == 0) and cell * D a multiple of 8: the stores are aligned
         if (FULL || nvalid == NR) {
             uint32_t w[NR / 2];
 #pragma unroll
             for (int k = 0; k < NR / 2; k++) w[k] = __byte_perm(q[2 * k], q[2 * k + 1], 0x6420);
-            if constexpr (FULL && NR == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
-            else if constexpr (FULL && NR == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-            else {
+            if constexpr (FULL && NR % 8 == 0) {
+#pragma unroll
+                for (int k = 0; k < NR / 8; k++) reinterpret_cast<uint4 *>(dst)[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            } else if constexpr (NR % 4 == 0) {
+#pragma unroll
+                for (int k = 0; k < NR / 4; k++) reinterpret_cast<uint2 *>(dst)[k] = make_uint2(w[2 * k], w[2 * k + 1]);
+            } else {
 #pragma unroll
                 for (int k = 0; k < NR / 2; k++) reinterpret_cast<uint32_t *>(dst)[k] = w[k];
             }
@@ -269,24 +284,27 @@ template <int NR, int LPC, bool FULL> struct ChainRun {
     static constexpr unsigned kRingBytes = kRing * kSlotBytes;
     // the two chains of a warp read their rings in the same instruction: offset the second ring by 16 banks
     static constexpr unsigned kChainPitch = kRingBytes + ((kRingBytes % 128 == 0 && LPC < 32) ? 64 : 0);
+    // FULL (D == LPC * 2NR, a multiple of 16): 16-byte copies, LPC * NR / 8 of them per cell; otherwise 8-byte copies
     static constexpr int kRounds = (NR + 3) / 4;    // 8-byte cp.async rounds: LPC lanes fetch LPC * 8 bytes per round
-    static constexpr int kRounds16 = (NR + 7) / 8;  // 16-byte rounds (D % 16 == 0)
+    static constexpr int kRounds16 = (NR + 7) / 8;  // 16-byte rounds
     const uint8_t *fused_lane; // fused + sl * 8 (or sl * 16)
     uint8_t *q_lane;           // path volume + sl * 2NR
     unsigned ring_ld;          // shared address of the chain's ring + sl * 2NR (reads)
     unsigned ring_st;          // shared address of the chain's ring + sl * 8 (or sl * 16): cp.async destination
     int D, sl;
-    bool wide;                 // D % 16 == 0: 16-byte copies
+    unsigned on16[kRounds16];  // FULL: does this lane copy in round r
     unsigned rd_off = 0;                           // ring slot of the step being consumed
     unsigned wr_off = (kRing - 1) * kSlotBytes;    // free slot: the one consumed in the previous step
 
     __device__ __forceinline__ void issue(unsigned slot_off, int off8) const
     {
         const uint8_t *src = fused_lane + (long long)off8 * 8;
-        if (wide) {
+        if constexpr (FULL) {
 #pragma unroll
-            for (int r = 0; r < kRounds16; r++)
-                if ((sl + r * LPC) * 16 < D) cp_async16(ring_st + slot_off + r * LPC * 16, src + r * LPC * 16);
+            for (int r = 0; r < kRounds16; r++) {
+                if ((r + 1) * LPC * 16 <= LPC * 2 * NR) cp_async16(ring_st + slot_off + r * LPC * 16, src + r * LPC * 16);
+                else cp_async16_if(ring_st + slot_off + r * LPC * 16, src + r * LPC * 16, on16[r]);
+            }
         } else {
 #pragma unroll
             for (int r = 0; r < kRounds; r++)
@@ -298,7 +316,17 @@ template <int NR, int LPC, bool FULL> struct ChainRun {
         cp_async_wait<kRing - 2>();
         __syncwarp();
         const unsigned src = ring_ld + rd_off;
-        if constexpr (NR % 2 == 0) {
+        if constexpr (NR % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < NR / 4; k++) {
+                uint32_t v0, v1;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v0), "=r"(v1) : "r"(src + 8 * k) : "memory");
+                c[4 * k] = __byte_perm(v0, 0u, 0x4140);
+                c[4 * k + 1] = __byte_perm(v0, 0u, 0x4342);
+                c[4 * k + 2] = __byte_perm(v1, 0u, 0x4140);
+                c[4 * k + 3] = __byte_perm(v1, 0u, 0x4342);
+            }
+        } else if constexpr (NR % 2 == 0) {
 #pragma unroll
             for (int k = 0; k < NR / 2; k++) {
                 uint32_t v;
@@ -333,15 +361,17 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CPW = 32 / LPC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    LaneInfo li;
+    LaneInfo<LPC> li;
     li.sl = lane % LPC;
-    li.sub = lane / LPC;
-    li.first_lane = li.sl == 0;
-    li.last_lane = li.sl == LPC - 1;
+    const int sub = lane / LPC;
+    li.up_mask = li.sl == 0 ? kInf2 : 0u;
+    li.dn_mask = li.sl == LPC - 1 ? kInf2 : 0u;
+#pragma unroll
+    for (int g = 0; g < CPW; g++) li.others[g] = (g == sub) ? 0u : 0x7FFF7FFFu;
     const Sections sec = chain_sections(d, CPW);
     Chain ch;
     int nsteps = 0;
-    const int kind = chain_decode(d, sec, ((long long)blockIdx.x * kChainWarps + warp) * CPW + li.sub, ch, nsteps);
+    const int kind = chain_decode(d, sec, ((long long)blockIdx.x * kChainWarps + warp) * CPW + sub, ch, nsteps);
     if (kind < 0) return; // warp-uniform: sections are padded to whole warps
     const int D = d.D, Wp = d.Wp;
     using Run = ChainRun<NR, LPC, FULL>;
@@ -349,13 +379,14 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
     run.D = D;
     run.sl = li.sl;
     li.nvalid = FULL ? NR : lane_nvalid<NR>(D, li.sl);
-    run.wide = (D & 15) == 0;
-    run.fused_lane = fused + li.sl * (run.wide ? 16 : 8);
+    run.fused_lane = fused + li.sl * (FULL ? 16 : 8);
+#pragma unroll
+    for (int r = 0; r < Run::kRounds16; r++) run.on16[r] = ((li.sl + r * LPC) * 16 < D) ? 1u : 0u;
     run.q_lane = qvol + (size_t)ch.vol * (size_t)d.cells + li.sl * 2 * NR;
     {
-        const unsigned base = (unsigned)__cvta_generic_to_shared(smem_raw + ((size_t)warp * CPW + li.sub) * Run::kChainPitch);
+        const unsigned base = (unsigned)__cvta_generic_to_shared(smem_raw + ((size_t)warp * CPW + sub) * Run::kChainPitch);
         run.ring_ld = base + li.sl * 2 * NR;
-        run.ring_st = base + li.sl * (run.wide ? 16 : 8);
+        run.ring_st = base + li.sl * (FULL ? 16 : 8);
     }
     const int nvalid = li.nvalid;
     const int D8 = D >> 3;
@@ -537,23 +568,22 @@ static void launch_paths(const uint8_t *fused, const Dims &d, uint8_t *qvol, cud
     k_sgm_paths<NR, LPC, FULL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, smem, st>>>(fused, d, qvol);
 }
 
-template <int LPC>
+template <int LPC, int NRMAX>
 static void launch_paths_lpc(const uint8_t *fused, const Dims &d, uint8_t *qvol, cudaStream_t st)
 {
     const int nr = (d.D + 2 * LPC - 1) / (2 * LPC); // disparities per lane = 2 * NR, chosen so that D fits in LPC lanes
     const bool full = d.D == 2 * LPC * nr;
 #define SISTER_PATHS_CASE(N)                                                                    \
     case N:                                                                                     \
-        if (full) launch_paths<N, LPC, true>(fused, d, qvol, st);                               \
-        else launch_paths<N, LPC, false>(fused, d, qvol, st);                                   \
+        if constexpr (N <= NRMAX) {                                                             \
+            if (full) launch_paths<N, LPC, true>(fused, d, qvol, st);                           \
+            else launch_paths<N, LPC, false>(fused, d, qvol, st);                               \
+        }                                                                                       \
         break;
     switch (nr) {
         SISTER_PATHS_CASE(1) SISTER_PATHS_CASE(2) SISTER_PATHS_CASE(3) SISTER_PATHS_CASE(4)
-        SISTER_PATHS_CASE(5) SISTER_PATHS_CASE(6) SISTER_PATHS_CASE(7)
-    default:
-        if (full) launch_paths<8, LPC, true>(fused, d, qvol, st);
-        else launch_paths<8, LPC, false>(fused, d, qvol, st);
-        break;
+        SISTER_PATHS_CASE(5) SISTER_PATHS_CASE(6) SISTER_PATHS_CASE(7) SISTER_PATHS_CASE(8)
+        SISTER_PATHS_CASE(9) SISTER_PATHS_CASE(10) SISTER_PATHS_CASE(11) SISTER_PATHS_CASE(12)
     }
 #undef SISTER_PATHS_CASE
 }
@@ -562,8 +592,9 @@ void launch_sgm(const uint8_t *fused, const Dims &d, uint8_t *qvol, uint16_t *su
                 int *status, cudaStream_t st, LaunchCounter &lc)
 {
     (void)status;
-    if (d.D <= 256) launch_paths_lpc<16>(fused, d, qvol, st); // two chains per warp
-    else launch_paths_lpc<32>(fused, d, qvol, st);
+    if (d.D <= 192) launch_paths_lpc<8, 12>(fused, d, qvol, st);        // four chains per warp
+    else if (d.D <= 256) launch_paths_lpc<16, 8>(fused, d, qvol, st);   // two chains per warp
+    else launch_paths_lpc<32, 8>(fused, d, qvol, st);
     lc.add();
     const long long groups = (d.px + 3) / 4;
     long long blocks = (groups + 7) / 8;
