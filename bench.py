@@ -312,7 +312,7 @@ def main():
         "gcost_evals_per_s": fps * evals / 1e9,
         "config": {"workload": WORKLOAD, "rigs_per_step_per_gpu": B, "rigs_in_flight_per_gpu": S, "evals_per_frame": evals,
                    "padded_cells_per_frame": cells, "sharding": "by frame, no data-path collective" + ("; NCCL gather of maps to rank 0" if world > 1 else ""),
-                   "l2": "per-frame working set (fused 0.43 GB + sum 0.86 GB) exceeds the 126 MB L2; no flush needed"},
+                   "l2": "per-frame working set (fused 0.43 GB + 8 path volumes 3.4 GB) exceeds the 126 MB L2; no flush needed"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "stage_ms_single_rig": stages_acc, "single_rig_latency_ms": sum(stages_acc.values()),
     }

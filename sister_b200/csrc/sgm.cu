@@ -188,31 +188,32 @@ struct Chain {
     int vol;        // path volume index: 4 * pass + path
 };
 
-// Chain numbering, four sections, each padded to a multiple of `cpw` (chains per warp) so that a warp never mixes
+// Chain numbering, three sections, each padded to a multiple of `cpw` (chains per warp) so that a warp never mixes
 // kinds; a padding slot repeats the section's last chain (it recomputes and rewrites the same bytes):
 //   kind 1  [2]              r0 on the first line of pass 0 / pass 1
 //   kind 0  [2 * (Hp-1)]     r0 on the other rows
-//   kind 2  [2 * Wp]         r2 columns
-//   kind 3  [4 * Wp]         r1 / r3 wrapped diagonals
+//   kind 2  [6 * Wp]         r1, r2, r3 of a pass, ordered [pass][column][path]: the three top-down (bottom-up) paths
+//                            of neighbouring columns share warps, advance in lock step and therefore read every row
+//                            of C within a few steps of each other -- two of the three reads hit L2
 struct Sections {
-    long long n[4], o[5];
+    long long n[3], o[4];
 };
 __host__ __device__ inline Sections chain_sections(const Dims &d, int cpw)
 {
     Sections s;
-    const long long cnt[4] = {2, 2LL * (d.Hp - 1), 2LL * d.Wp, 4LL * d.Wp};
+    const long long cnt[3] = {2, 2LL * (d.Hp - 1), 6LL * d.Wp};
     s.o[0] = 0;
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 3; k++) {
         s.n[k] = cnt[k];
         s.o[k + 1] = s.o[k] + (cnt[k] + cpw - 1) / cpw * cpw;
     }
     return s;
 }
 
-// returns the kind (0..3) or -1 when g is past the end
+// returns the kind (0..2) or -1 when g is past the end
 __device__ __forceinline__ int chain_decode(const Dims &d, const Sections &sec, long long g, Chain &ch, int &nsteps)
 {
-    if (g >= sec.o[4]) return -1;
+    if (g >= sec.o[3]) return -1;
     if (g < sec.o[1]) {
         const int p = (int)min(g, sec.n[0] - 1);
         ch.i = p ? d.Hp - 1 : 0; ch.j = p ? d.Wp - 1 : 0; ch.si = 0; ch.sj = p ? -1 : 1; ch.enter = 0;
@@ -226,22 +227,15 @@ __device__ __forceinline__ int chain_decode(const Dims &d, const Sections &sec, 
         ch.vol = 4 * p; nsteps = d.Wp;
         return 0;
     }
-    if (g < sec.o[3]) {
-        const long long idx = min(g - sec.o[2], sec.n[2] - 1);
-        const int p = (int)(idx / d.Wp), col = (int)(idx % d.Wp);
-        ch.i = p ? d.Hp - 1 : 0; ch.j = col; ch.si = p ? -1 : 1; ch.sj = 0; ch.enter = 0;
-        ch.vol = 4 * p + 2; nsteps = d.Hp;
-        return 2;
-    }
-    const long long idx = min(g - sec.o[3], sec.n[3] - 1);
-    const int p = (int)(idx / (2LL * d.Wp));
-    const int rem = (int)(idx % (2LL * d.Wp)), col = rem >> 1, r3 = rem & 1;
+    const long long idx = min(g - sec.o[2], sec.n[2] - 1);
+    const int p = (int)(idx / (3LL * d.Wp));
+    const int rem = (int)(idx % (3LL * d.Wp)), col = rem / 3, type = rem % 3; // 0: r1, 1: r2, 2: r3
     const int dj = p ? -1 : 1, j1 = p ? d.Wp - 1 : 0, jl = p ? 0 : d.Wp - 1;
     ch.i = p ? d.Hp - 1 : 0; ch.j = col; ch.si = dj;
-    ch.sj = r3 ? -dj : dj;
-    ch.enter = r3 ? jl : j1;
-    ch.vol = 4 * p + (r3 ? 3 : 1); nsteps = d.Hp;
-    return 3;
+    ch.sj = type == 0 ? dj : type == 1 ? 0 : -dj;
+    ch.enter = type == 0 ? j1 : jl; // unused by r2 (sj = 0 never leaves the frame)
+    ch.vol = 4 * p + 1 + type; nsteps = d.Hp;
+    return 2;
 }
 
 // ---------------------------------------------------------------------------------------------- the path kernel
@@ -398,7 +392,7 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
 
     // prologue: kRing - 1 steps in flight
     int poff = first8, pj = ch.j;
-    const bool diag = kind == 3;
+    const bool diag = kind == 2; // columns ride along in the wrapped-diagonal loop (sj = 0 never wraps)
 #pragma unroll 1
     for (int t = 0; t < kRing - 1; t++) {
         run.issue(t * Run::kSlotBytes, poff); // nsteps >= 12 (check_shape, sister_test_sgm)
@@ -426,25 +420,13 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
             poff += stride8;
         }
     } else if (!diag) {
-        // ---- rows (r0, a = 0 at the start of the row, sgm.cpp:215-216) and columns (r2): no border crossing ----
+        // ---- rows (r0, a = 0 at the start of the row, sgm.cpp:215-216): no border crossing ----
         // the store cursor is the prefetch cursor kRing - 1 steps ago: fold the lag into the base pointer
         uint8_t *qlag = run.q_lane - (long long)(kRing - 1) * stride8 * 8;
-        int s = 0;
-        if (kind == 2) {
-            run.consume(c);
-            const unsigned wr = run.advance_ring();
-            run.issue(wr, poff);
-            cp_async_commit();
-            chain_first_cell<NR, LPC, FULL>(a, c, li, q);
-            store_q<NR, FULL>(qlag + (long long)poff * 8, q, nvalid);
-            poff += stride8;
-            s = 1;
-        } else {
 #pragma unroll
-            for (int k = 0; k < NR; k++) a[k] = (k < nvalid) ? 0u : kInf2;
-        }
+        for (int k = 0; k < NR; k++) a[k] = (k < nvalid) ? 0u : kInf2;
 #pragma unroll 1
-        for (; s < nsteps; s++) {
+        for (int s = 0; s < nsteps; s++) {
             run.consume(c);
             const unsigned wr = run.advance_ring();
             if (s < n_issue) run.issue(wr, poff);
@@ -454,7 +436,7 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
             poff += stride8;
         }
     } else {
-        // ---- diagonals (r1, r3): wrapped chains, a = P2 after a border crossing (sgm.cpp:57-81) ----
+        // ---- columns (r2) and diagonals (r1, r3): wrapped chains, a = P2 after a border crossing (sgm.cpp:57-81) ----
         int qoff = first8, j = ch.j;
         {
             run.consume(c);
@@ -563,7 +545,7 @@ static void launch_paths(const uint8_t *fused, const Dims &d, uint8_t *qvol, cud
         cudaFuncSetAttribute(k_sgm_paths<NR, LPC, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
-    const long long n = chain_sections(d, CPW).o[4];
+    const long long n = chain_sections(d, CPW).o[3];
     const long long per_block = (long long)kChainWarps * CPW;
     k_sgm_paths<NR, LPC, FULL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, smem, st>>>(fused, d, qvol);
 }
