@@ -27,6 +27,8 @@
 // 40 B for the path-by-path accumulation into a uint16 sum volume this replaces. The fused-cost rows a chain will
 // need are known in advance, so each warp keeps kRing steps of C in flight with cp.async (LDGSTS) into a private
 // shared-memory ring; nothing in a chain step waits on DRAM.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace sister {
@@ -71,18 +73,16 @@ template <int NR> __device__ __forceinline__ int lane_nvalid(int D, int sl)
 // with equal halves the unsigned 32-bit order is the 16-bit order and one CREDUX.MIN per chain does it.
 template <int LPC> __device__ __forceinline__ uint32_t chain_min2(uint32_t m2, const uint32_t (&others)[32 / LPC])
 {
-    // others[g] = 0x7FFF7FFF when this lane is NOT in chain g of the warp, 0 when it is
-    const uint32_t v = __vmins2(m2, __byte_perm(m2, m2, 0x1032));
+    (void)others;
+    uint32_t v = __vmins2(m2, __byte_perm(m2, m2, 0x1032));
     if constexpr (LPC == 32) {
         return __reduce_min_sync(kFull, v);
     } else {
-        uint32_t r = 0;
+        // xor-butterfly inside the chain's LPC lanes: log2(LPC) shuffles serve every chain of the warp at once and the
+        // dependent latency is a few shuffles instead of one CREDUX per chain
 #pragma unroll
-        for (int g = 0; g < 32 / LPC; g++) {
-            const uint32_t mg = __reduce_min_sync(kFull, v | others[g]); // lanes outside chain g contribute 0x7FFF7FFF
-            r |= mg & ~others[g];                                        // (x & ~0x7FFF7FFF) == 0 for x <= 0x3FFF3FFF
-        }
-        return r;
+        for (int o = 1; o < LPC; o <<= 1) v = __vmins2(v, __shfl_xor_sync(kFull, v, o));
+        return v;
     }
 }
 
@@ -350,7 +350,7 @@ template <int NR, int LPC, bool FULL> struct ChainRun {
 
 // grid ceil(chains / (kChainWarps * 32 / LPC)), block kChainWarps * 32, dynamic smem kChainWarps * kRing * 64 * NR bytes
 template <int NR, int LPC, bool FULL>
-__global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, uint8_t *__restrict__ qvol)
+__global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, uint8_t *__restrict__ qvol, unsigned kind_mask)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CPW = 32 / LPC;
@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
     int nsteps = 0;
     const int kind = chain_decode(d, sec, ((long long)blockIdx.x * kChainWarps + warp) * CPW + sub, ch, nsteps);
     if (kind < 0) return; // warp-uniform: sections are padded to whole warps
+    if (!((kind_mask >> kind) & 1u)) return; // measurement aid (SISTER_DEBUG_PATH_KINDS), always 7 in the product
     const int D = d.D, Wp = d.Wp;
     using Run = ChainRun<NR, LPC, FULL>;
     Run run;
@@ -451,10 +452,12 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_sgm_paths(const uint8_t *_
             poff += stride8; pj += ch.sj;
             if ((unsigned)pj >= (unsigned)Wp) { pj = ch.enter; poff += wrapfix8; }
             qoff += stride8; j += ch.sj;
-            if ((unsigned)j >= (unsigned)Wp) {
-                j = ch.enter; qoff += wrapfix8;
+            const bool wrapped = (unsigned)j >= (unsigned)Wp;
+            if (wrapped) { j = ch.enter; qoff += wrapfix8; }
+            if (__any_sync(kFull, wrapped)) { // rare (once per chain): keep the per-register selects off the common path
 #pragma unroll
-                for (int k = 0; k < NR; k++) a[k] = (FULL || k < nvalid) ? kP2x2 : kInf2;
+                for (int k = 0; k < NR; k++)
+                    if (wrapped) a[k] = (FULL || k < nvalid) ? kP2x2 : kInf2;
             }
             run.consume(c);
             const unsigned wr = run.advance_ring();
@@ -535,6 +538,14 @@ __global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ f
 
 // ---------------------------------------------------------------------------------------------- launch
 
+// measurement aid: SISTER_DEBUG_PATH_KINDS=<bit mask of chain kinds to run> (results are then incomplete)
+static unsigned path_kind_mask()
+{
+    static int m = -1;
+    if (m < 0) { const char *e = getenv("SISTER_DEBUG_PATH_KINDS"); m = e ? atoi(e) & 7 : 7; }
+    return (unsigned)m;
+}
+
 template <int NR, int LPC, bool FULL>
 static void launch_paths(const uint8_t *fused, const Dims &d, uint8_t *qvol, cudaStream_t st)
 {
@@ -547,7 +558,7 @@ static void launch_paths(const uint8_t *fused, const Dims &d, uint8_t *qvol, cud
     }
     const long long n = chain_sections(d, CPW).o[3];
     const long long per_block = (long long)kChainWarps * CPW;
-    k_sgm_paths<NR, LPC, FULL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, smem, st>>>(fused, d, qvol);
+    k_sgm_paths<NR, LPC, FULL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, smem, st>>>(fused, d, qvol, path_kind_mask());
 }
 
 template <int LPC, int NRMAX>

@@ -159,7 +159,8 @@ int main(int argc, char **argv)
     for (size_t p = 0; p < (size_t)w * h; p++)
         for (int c = 0; c < 3; c++) {
             const float a = ch == 3 ? v[0].px[3 * p + c] : v[0].px[p];
-            long r = std::lrintf(a * alpha + colored[0][3 * p + c] * (1.0f - alpha));
+            // OpenCV's 8-bit addWeighted works in float: fma(a, alpha, b * beta) on its SIMD path
+            long r = std::lrintf(std::fmaf(a, alpha, colored[0][3 * p + c] * (1.0f - alpha)));
             blended[3 * p + c] = (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
         }
     if (!write_ppm_bgr(out + "blended.ppm", blended, w, h)) { fprintf(stderr, "cannot write to %s\n", out.c_str()); return 1; }
