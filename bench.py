@@ -264,6 +264,13 @@ def main():
     e2e = None
     if not args.no_e2e:
         outs = [[np.zeros((H_, W_), np.uint16), None, None] for _ in range(B)]
+        # the step's inputs live in page-locked host memory (what a capture pipeline hands over); the H2D copy of every
+        # view and the D2H copy of every map are inside the timed region
+        pinned = eng.host_array((B, 5, H_, W_, 3), np.uint8)
+        for k in range(B):
+            for v in range(5):
+                pinned[k, v] = rigs_bgr[k][v]
+        rigs_bgr = [[pinned[k, v] for v in range(5)] for k in range(B)]
         for _ in range(2):
             eng.compute_batch(rigs_bgr, D_, sister_b200.MODE_MULTIVIEW, outs=outs)
         barrier()
@@ -277,7 +284,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dt = float(te.item())
         e2e = {"value": world * B * args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": B * 5 * W_ * H_ * 3,
-               "d2h_bytes_per_step": B * W_ * H_ * 2, "input": "BGR uint8 (cv::imread layout)", "checksum": checksum}
+               "d2h_bytes_per_step": B * W_ * H_ * 2, "input": "BGR uint8 (cv::imread layout), page-locked host memory", "checksum": checksum}
         # parity guard: the e2e path and the device path must agree
         same = bool((torch.from_numpy(outs[0][0].astype(np.int32)).to(dev) == (out_t[0].to(torch.int32) & 0xFFFF)).all().item())
         e2e["matches_device_path"] = same
@@ -300,7 +307,14 @@ def main():
     agg_ms = statistics.median(agg)
     algo_bytes = 8 * cells  # read C twice, write S once, read S once, per padded cell, uint16 volumes
     achieved = algo_bytes / (agg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes of the same launch group from the committed ncu --set full capture (per frame, like `achieved`)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic, traffic_src = tj["aggregation_dram_bytes_per_frame"], "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "traffic_gbs": (traffic / (agg_ms * 1e-3) / 1e9) if traffic else None,
                 "kernel": "aggregation passes (SGM, sgm.cpp:26-455)", "algorithmic_bytes_per_launch_group": algo_bytes,
                 "launches_in_group": stage_launches["aggregate"], "duration_ms": agg_ms, "peak_source": peak_src,
                 "how": "CUDA events on the slot stream around the aggregation kernels, 1 rig in flight, median of 4"}

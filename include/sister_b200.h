@@ -102,6 +102,11 @@ int sister_sync(sister_ctx *ctx, int slot); /* slot < 0: all slots */
 /* Plain device memory helpers so that a host language needs no CUDA binding of its own. */
 int sister_dev_alloc(sister_ctx *ctx, size_t bytes, void **dev_ptr);
 int sister_dev_free(sister_ctx *ctx, void *dev_ptr);
+/* Page-locked host memory. sister_submit / sister_compute(_batch) copy a dense view that lives in page-locked memory
+ * (from here, cudaHostAlloc or cudaHostRegister) to the device directly; other buffers are staged through the slot's
+ * own pinned area with one extra memcpy. */
+int sister_host_alloc(sister_ctx *ctx, size_t bytes, void **host_ptr);
+int sister_host_free(sister_ctx *ctx, void *host_ptr);
 int sister_dev_upload(sister_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes);
 int sister_dev_download(sister_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes);
 

@@ -21,7 +21,7 @@ _i16p = C.POINTER(C.c_int16)
 # every symbol include/sister_b200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = (
     "sister_create", "sister_destroy", "sister_compute", "sister_compute_batch", "sister_submit", "sister_wait",
-    "sister_submit_device", "sister_sync", "sister_dev_alloc", "sister_dev_free", "sister_dev_upload",
+    "sister_submit_device", "sister_sync", "sister_dev_alloc", "sister_dev_free", "sister_host_alloc", "sister_host_free", "sister_dev_upload",
     "sister_dev_download", "sister_set_profiling", "sister_region_begin", "sister_region_end", "sister_get_stage_ms", "sister_get_stage_launches",
     "sister_get_launch_count", "sister_debug_fetch", "sister_set_test_taps", "sister_test_sgm", "sister_strerror", "sister_last_error",
     "sister_version",
@@ -79,6 +79,10 @@ def load_library():
     L.sister_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.sister_dev_free.restype = C.c_int
     L.sister_dev_free.argtypes = [vp, vp]
+    L.sister_host_alloc.restype = C.c_int
+    L.sister_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.sister_host_free.restype = C.c_int
+    L.sister_host_free.argtypes = [vp, vp]
     L.sister_dev_upload.restype = C.c_int
     L.sister_dev_upload.argtypes = [vp, vp, vp, C.c_size_t]
     L.sister_dev_download.restype = C.c_int
@@ -124,6 +128,7 @@ class Engine:
         self.n_slots = n_slots
         self._chk(self.lib.sister_create(C.byref(self.ctx), device, max_w, max_h, max_disp, n_slots), create=True)
         self._dev_allocs = []
+        self._host_allocs = []
 
     # -- plumbing
     def _chk(self, rc: int, create: bool = False):
@@ -135,6 +140,9 @@ class Engine:
 
     def close(self):
         if getattr(self, "ctx", None):
+            for p in getattr(self, "_host_allocs", []):
+                self.lib.sister_host_free(self.ctx, C.c_void_p(p))
+            self._host_allocs = []
             self.lib.sister_destroy(self.ctx)
             self.ctx = None
 
@@ -202,6 +210,16 @@ class Engine:
 
     def dev_free(self, ptr: int):
         self._chk(self.lib.sister_dev_free(self.ctx, C.c_void_p(ptr)))
+
+    def host_array(self, shape, dtype=np.uint8) -> np.ndarray:
+        """A numpy array in page-locked host memory (sister_host_alloc); views passed from it skip the staging memcpy.
+        The memory belongs to the engine and is released by close()."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._chk(self.lib.sister_host_alloc(self.ctx, nbytes, C.byref(p)))
+        self._host_allocs.append(p.value)
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def dev_upload(self, ptr: int, a: np.ndarray):
         a = np.ascontiguousarray(a)

@@ -282,18 +282,28 @@ int sister_submit(sister_ctx *ctx, int slot, const uint8_t *const views[5], int 
     SCK(cudaSetDevice(ctx->device));
     const size_t row = (size_t)w * channels, view_bytes = row * h;
     for (int k = 0; k < 5; k++) {
-        uint8_t *dst = s.h_in + k * view_bytes;
-        if (row_stride == row) memcpy(dst, views[k], view_bytes);
-        else for (int i = 0; i < h; i++) memcpy(dst + i * row, views[k] + i * row_stride, row);
+        // a dense view in page-locked memory (sister_host_alloc, cudaHostAlloc, cudaHostRegister) is copied straight from
+        // the caller's buffer; anything else goes through the slot's pinned staging area first
+        const uint8_t *src = views[k];
+        cudaPointerAttributes attr;
+        const bool pinned = row_stride == row && cudaPointerGetAttributes(&attr, views[k]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) {
+            cudaGetLastError(); // a failed query must not poison the stream of error checks
+            uint8_t *dst = s.h_in + k * view_bytes;
+            if (row_stride == row) memcpy(dst, views[k], view_bytes);
+            else for (int i = 0; i < h; i++) memcpy(dst + i * row, views[k] + i * row_stride, row);
+            src = dst;
+        }
+        SCK(cudaMemcpyAsync(s.d_in + k * view_bytes, src, view_bytes, cudaMemcpyHostToDevice, s.st));
     }
-    SCK(cudaMemcpyAsync(s.d_in, s.h_in, 5 * view_bytes, cudaMemcpyHostToDevice, s.st));
     const uint8_t *dv[5];
     for (int k = 0; k < 5; k++) dv[k] = s.d_in + k * view_bytes;
     const size_t wh = (size_t)w * h;
     uint16_t *od[3] = {s.d_out, s.d_out + wh, s.d_out + 2 * wh};
     rc = run_pipeline(ctx, s, dv, (int)row, channels, d, mode_mask, od);
     if (rc) return rc;
-    SCK(cudaMemcpyAsync(s.h_out, s.d_out, 3 * wh * 2, cudaMemcpyDeviceToHost, s.st));
+    for (int m = 0; m < 3; m++)
+        if (mode_mask & (1u << m)) SCK(cudaMemcpyAsync(s.h_out + m * wh, s.d_out + m * wh, wh * 2, cudaMemcpyDeviceToHost, s.st));
     s.busy = true;
     s.host_io = true;
     return SISTER_OK;
@@ -392,6 +402,20 @@ int sister_dev_free(sister_ctx *ctx, void *dev_ptr)
     if (!ctx) return SISTER_E_ARG;
     SCK(cudaSetDevice(ctx->device));
     SCK(cudaFree(dev_ptr));
+    return SISTER_OK;
+}
+int sister_host_alloc(sister_ctx *ctx, size_t bytes, void **host_ptr)
+{
+    if (!ctx || !host_ptr) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    SCK(cudaHostAlloc(host_ptr, bytes, cudaHostAllocDefault));
+    return SISTER_OK;
+}
+int sister_host_free(sister_ctx *ctx, void *host_ptr)
+{
+    if (!ctx) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    SCK(cudaFreeHost(host_ptr));
     return SISTER_OK;
 }
 int sister_dev_upload(sister_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes)

@@ -195,3 +195,17 @@ def test_config4_large_frame_single_gpu():
     assert (a == b).all()
     inner = a[64:-64, 64:-64] // 255
     assert (inner == int(round(D / 3.0))).mean() > 0.9
+
+
+def test_pinned_and_strided_inputs(engine):
+    """Views in page-locked memory are copied to the device directly, pageable or row-padded ones are staged: same maps."""
+    g = np.load(os.path.join(GOLDEN, "rig_96x64_d32.npz"))
+    w, h, D = int(g["w"]), int(g["h"]), int(g["D"])
+    views = make_rig(w, h, D, seed=int(g["seed"]), kind=str(g["kind"]), channels=3)
+    pinned = engine.host_array((5, h, w, 3), np.uint8)
+    for k in range(5):
+        pinned[k] = views[k]
+    a = engine.compute([pinned[k] for k in range(5)], D, mode_mask=1)[0]
+    assert (a == g["disp_mv"]).all()
+    batch = engine.compute_batch([[pinned[k] for k in range(5)]] * 3, D, mode_mask=1)
+    assert all((b[0] == g["disp_mv"]).all() for b in batch)
