@@ -1,5 +1,4 @@
-// sister_b200 / sgm_core.cuh -- the per-step arithmetic of the semi-global aggregation, shared by the chain kernel
-// (sgm.cu) and the lock-step pair sweeps (sweep.cu). See the header comment of sgm.cu for the formulation
+// sister_b200 / sgm_core.cuh -- the per-step arithmetic of the semi-global aggregation, of the chain kernel (sgm.cu). See the header comment of sgm.cu for the formulation
 // (normalised clamped state a, penalty byte Q = L' - C) and its mapping to sgm.cpp:26-455.
 #pragma once
 #include "kernels.cuh"
@@ -9,254 +8,265 @@ namespace sister {
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint32_t kP1x2 = (uint32_t)kP1 * 0x10001u;
 constexpr uint32_t kP2x2 = (uint32_t)kP2 * 0x10001u;
-constexpr int kRing = 12;         // steps of fused cost in flight per chain
-
-// Lane mapping. A chain occupies LPC lanes of a warp (LPC = 16 for D <= 256: two chains per warp, so the per-step
-// fixed work -- shuffles, border selects, the min reduction, loop and cursor arithmetic -- is paid once for two
-// chains; LPC = 32 above). Lane sl of a chain owns the 2 * NR consecutive disparities sl * 2NR ..., two per register.
-
-// ---------------------------------------------------------------------------------------------- small helpers
-
-__device__ __forceinline__ void cp_async8(unsigned smem_dst, const void *gmem_src)
+// make a value opaque to the optimiser (no rematerialisation from its definition)
+__device__ __forceinline__ void opaque(unsigned &x) { asm volatile("mov.u32 %0, %0;\n" : "+r"(x)); }
+template <class T> __device__ __forceinline__ void opaque_ptr(T *&p)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gmem_src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
-}
-// the same, issued only by lanes whose `on` register is non-zero (a register predicate keeps ptxas from
-// re-deriving the lane test from %tid in every step)
-__device__ __forceinline__ void cp_async16_if(unsigned smem_dst, const void *gmem_src, unsigned on)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n" ::"r"(smem_dst), "l"(gmem_src), "r"(on) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-// number of valid packed registers of this lane (disparities sl*2NR + 2k, +1 are valid for k < nvalid)
-template <int NR> __device__ __forceinline__ int lane_nvalid(int D, int sl)
-{
-    int n = D / 2 - sl * NR;
-    return n < 0 ? 0 : (n > NR ? NR : n);
+    unsigned long long v = reinterpret_cast<unsigned long long>(p);
+    asm volatile("mov.u64 %0, %0;\n" : "+l"(v));
+    p = reinterpret_cast<T *>(v);
 }
 
-// min over the chain's lanes of both halves of m2, returned in both halves: (m, m). All values are in [0, 0x3FFF], so
-// with equal halves the unsigned 32-bit order is the 16-bit order and one CREDUX.MIN per chain does it.
-template <int LPC> __device__ __forceinline__ uint32_t chain_min2(uint32_t m2, const uint32_t (&others)[32 / LPC])
+// min over the chain's lanes of both halves of m2, returned in both halves: (m, m). Xor-butterfly inside the chain's LPC
+// lanes: log2(LPC) shuffles serve every chain of the warp at once. (One CREDUX.MIN per chain with the other chains
+// masked out has a shorter dependent latency but costs more issue slots; measured no faster on B200.)
+template <int LPC> __device__ __forceinline__ uint32_t chain_min2(uint32_t m2)
 {
-    (void)others;
     uint32_t v = __vmins2(m2, __byte_perm(m2, m2, 0x1032));
     if constexpr (LPC == 32) {
         return __reduce_min_sync(kFull, v);
     } else {
-        // xor-butterfly inside the chain's LPC lanes: log2(LPC) shuffles serve every chain of the warp at once and the
-        // dependent latency is a few shuffles instead of one CREDUX per chain
 #pragma unroll
         for (int o = 1; o < LPC; o <<= 1) v = __vmins2(v, __shfl_xor_sync(kFull, v, o));
         return v;
     }
 }
 
-// Neighbour registers of a packed state vector: E[k] = (d-1 of the low half, low half), E[k+1] = (high half, d+1 of
-// the high half). The two values that live in the adjacent lanes come by shuffle; at the chain's first / last lane
-// they are kInf2 (L(-1) = L(D) = 65535 in the reference, sgm.cpp:84-87).
-template <int NR> __device__ __forceinline__ void neighbours(const uint32_t (&a)[NR], uint32_t up_mask, uint32_t dn_mask, uint32_t (&E)[NR + 1])
-{
-    // up_mask / dn_mask = kInf2 at the chain's first / last lane, 0 elsewhere: x | kInf2 >= kInf2 never wins a minimum
-    const uint32_t up = __shfl_up_sync(kFull, a[NR - 1], 1) | up_mask;
-    const uint32_t dn = __shfl_down_sync(kFull, a[0], 1) | dn_mask;
-    E[0] = __byte_perm(up, a[0], 0x5432);
-#pragma unroll
-    for (int k = 1; k < NR; k++) E[k] = __byte_perm(a[k - 1], a[k], 0x5432);
-    E[NR] = __byte_perm(a[NR - 1], dn, 0x5432);
-}
+// Register layout of a chain's state ("split lanes"). Lane sl of a chain owns the 2 * NR consecutive disparities
+// d0 = sl * 2NR ...; register k holds the pair (d0 + k, d0 + NR + k) in its (low, high) 16-bit halves. The d-1 / d+1
+// neighbours of register k are then simply registers k-1 / k+1 -- whole registers, both halves at once -- and only the
+// two ends need a byte permute with a value from the adjacent lane:
+//     left of register 0       = (previous lane's high half of register NR-1, own low half of register NR-1)
+//     right of register NR-1   = (own high half of register 0, next lane's low half of register 0)
+// With b = a + P1 kept next to a, the penalty is ONE three-input packed minimum per register:
+//     Q[k] = min(a[k], b[k-1], b[k+1])                      (VIMNMX3.S16x2; reference: sgm.cpp:282-297)
+// At the chain's first / last lane the missing neighbour is kInf2 (L(-1) = L(D) = 65535, sgm.cpp:84-87). Disparities
+// >= D (only when D < LPC * 2NR, FULL = false) carry kInfHalf in a, b, L so that they never win a minimum.
+constexpr uint32_t kInfLo = 0x00003FFFu, kInfHi = 0x3FFF0000u;
 
-template <int LPC> struct LaneInfo {
-    int sl, nvalid;
-    uint32_t up_mask, dn_mask;       // kInf2 at the chain's first / last lane
-    uint32_t others[32 / LPC];       // 0x7FFF7FFF for the chains of the warp this lane does not belong to
+template <int NR, int LPC, bool FULL> struct LaneInfo {
+    int sl;                          // lane within the chain
+    uint32_t up_mask, dn_mask;       // kInf2 where the lane below / above holds no neighbour (chain ends, disparities >= D)
+    uint32_t pad[FULL ? 1 : NR];     // !FULL: kInfLo / kInfHi where the register's half is a disparity >= D
+    __device__ __forceinline__ void init(int lane, int D)
+    {
+        sl = lane % LPC;
+        up_mask = sl == 0 ? kInf2 : 0u;
+        dn_mask = (sl == LPC - 1 || (!FULL && (sl + 1) * 2 * NR >= D)) ? kInf2 : 0u;
+        if constexpr (!FULL) {
+#pragma unroll
+            for (int k = 0; k < NR; k++)
+                pad[k] = ((sl * 2 * NR + k >= D) ? kInfLo : 0u) | ((sl * 2 * NR + NR + k >= D) ? kInfHi : 0u);
+        } else {
+            pad[0] = 0u;
+        }
+    }
+    __device__ __forceinline__ uint32_t padded(uint32_t v, int k) const
+    {
+        if constexpr (FULL) return v;
+        else return v | pad[k];
+    }
+    // bytes of this lane's 2NR that lie inside the cell (a multiple of 4)
+    __device__ __forceinline__ int valid_bytes(int D) const
+    {
+        const int n = D - sl * 2 * NR;
+        return n < 0 ? 0 : (n > 2 * NR ? 2 * NR : n);
+    }
 };
 
-// One SGM step of one chain: a = clamped normalised state of the predecessor (pad registers = kInf2).
-// Writes q = L' - C (in [0, P2]) and the new state.
-template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ void chain_step(uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo<LPC> &li, uint32_t (&q)[NR])
+// the two end neighbours of b (see above)
+template <int NR> __device__ __forceinline__ void end_neighbours(const uint32_t (&b)[NR], uint32_t up_mask, uint32_t dn_mask, uint32_t &left, uint32_t &right)
 {
-    uint32_t E[NR + 1], L[NR];
-    neighbours<NR>(a, li.up_mask, li.dn_mask, E);
-    uint32_t m2 = kInf2;
-#pragma unroll
-    for (int k = 0; k < NR; k++) {
-        const uint32_t x = __viaddmin_s16x2(E[k], kP1x2, a[k]);
-        q[k] = __viaddmin_s16x2(E[k + 1], kP1x2, x);
-        L[k] = q[k] + c[k];
-        if (FULL || k < li.nvalid) m2 = __vmins2(m2, L[k]);
-    }
-    const uint32_t mm = chain_min2<LPC>(m2, li.others);
-    const uint32_t cap = mm + kP2x2;
-#pragma unroll
-    for (int k = 0; k < NR; k++) {
-        const uint32_t n = __vmins2(L[k], cap) - mm; // min(L - m, P2); L >= m in both halves, no borrow
-        a[k] = (FULL || k < li.nvalid) ? n : kInf2;
-    }
+    const uint32_t up = __shfl_up_sync(kFull, b[NR - 1], 1) | up_mask;
+    const uint32_t dn = __shfl_down_sync(kFull, b[0], 1) | dn_mask;
+    left = __byte_perm(up, b[NR - 1], 0x5432);
+    right = __byte_perm(b[0], dn, 0x5432);
 }
 
-// The first cell of a column / diagonal chain lies on the first line of the pass: L = C (sgm.cpp:103-138).
-template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ void chain_first_cell(uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo<LPC> &li, uint32_t (&q)[NR])
+// State of a chain between steps: a = min(L - m, P2) (clamped normalised costs), b = a + P1, and the two end
+// neighbours of b (left of register 0, right of register NR-1) already assembled for the next step.
+template <int NR> struct ChainState {
+    uint32_t a[NR], b[NR], left, right;
+};
+
+template <int NR> __device__ __forceinline__ uint32_t lane_min(const uint32_t (&L)[NR])
 {
-    uint32_t m2 = kInf2;
+    uint32_t m2 = __vmins2(L[0], L[1]);
+#pragma unroll
+    for (int k = 2; k < NR; k += 2) m2 = __vimin3_s16x2(m2, L[k], L[k + 1]);
+    return m2;
+}
+
+// normalise and clamp L into the next state. The end registers of L travel to the adjacent lanes BEFORE the minimum is
+// known (the shuffles overlap the reduction) and are normalised by the receiver: a step waits for one MIO round trip.
+// off_next: the NEXT cell of the chain follows a border crossing, its predecessor lies outside the frame: L_prev = 65535,
+// min = 0 in the reference (sgm.cpp:57-81), i.e. the state it must see is a = P2 everywhere. Adding a large positive
+// constant instead of -m makes every clamp below return exactly that, for one select per step.
+template <int NR, int LPC, bool FULL>
+__device__ __forceinline__ void renormalise(const uint32_t (&L)[NR], const LaneInfo<NR, LPC, FULL> &li, ChainState<NR> &st, bool off_next = false)
+{
+    const uint32_t up = __shfl_up_sync(kFull, L[NR - 1], 1);
+    const uint32_t dn = __shfl_down_sync(kFull, L[0], 1);
+    const uint32_t mm = chain_min2<LPC>(lane_min<NR>(L));
+    // -m as a 16-bit two's complement value in both halves (L <= 0x3FFF, so L + 0x3000 stays positive)
+    const uint32_t neg2 = off_next ? 0x30003000u : __byte_perm(0u - mm, 0u, 0x1010);
 #pragma unroll
     for (int k = 0; k < NR; k++) {
-        q[k] = 0u;
-        if (FULL || k < li.nvalid) m2 = __vmins2(m2, c[k]);
+        st.a[k] = li.padded(__viaddmin_s16x2(L[k], neg2, kP2x2), k);
+        st.b[k] = st.a[k] + kP1x2;
     }
-    const uint32_t mm = chain_min2<LPC>(m2, li.others);
-    const uint32_t cap = mm + kP2x2;
+    // a missing neighbour (mask = kInf2) normalises to P2 + P1, which no a <= P2 ever loses to: as good as infinity
+    const uint32_t bu = __viaddmin_s16x2(up | li.up_mask, neg2, kP2x2) + kP1x2;
+    const uint32_t bd = __viaddmin_s16x2(dn | li.dn_mask, neg2, kP2x2) + kP1x2;
+    st.left = __byte_perm(bu, st.b[NR - 1], 0x5432);
+    st.right = __byte_perm(st.b[0], bd, 0x5432);
+}
+
+// One SGM step of one chain. Writes q = L' - C (in [0, P2]) and the new state.
+template <int NR, int LPC, bool FULL>
+__device__ __forceinline__ void chain_step(ChainState<NR> &st, const uint32_t (&c)[NR], const LaneInfo<NR, LPC, FULL> &li, uint32_t (&q)[NR],
+                                           bool off_next = false)
+{
+    uint32_t L[NR];
 #pragma unroll
     for (int k = 0; k < NR; k++) {
-        const uint32_t n = __vmins2(c[k], cap) - mm;
-        a[k] = (FULL || k < li.nvalid) ? n : kInf2;
+        q[k] = __vimin3_s16x2(st.a[k], k == 0 ? st.left : st.b[k - 1], k == NR - 1 ? st.right : st.b[k + 1]);
+        L[k] = li.padded(q[k] + c[k], k);
     }
+    renormalise<NR, LPC, FULL>(L, li, st, off_next);
+}
+
+// constant state (a = v in every valid disparity): v = 0 at the start of a row for r0 (sgm.cpp:215-216), v = P2 behind
+// an off-image predecessor column (sgm.cpp:57-81)
+template <int NR, int LPC, bool FULL>
+__device__ __forceinline__ void chain_set(ChainState<NR> &st, uint32_t v2, const LaneInfo<NR, LPC, FULL> &li)
+{
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+        st.a[k] = li.padded(v2, k);
+        st.b[k] = st.a[k] + kP1x2;
+    }
+    st.left = __byte_perm((v2 + kP1x2) | li.up_mask, st.b[NR - 1], 0x5432);
+    st.right = __byte_perm(st.b[0], (v2 + kP1x2) | li.dn_mask, 0x5432);
 }
 
 // The horizontal path on the first line of a pass (sgm.cpp:141-190): plain int arithmetic on the un-normalised
 // values, then saturate_cast<uint16>(uint8) truncation (types.h:28). The state carried along the line is the truncated
-// value Lq and its minimum (mm, both halves); the byte written to the path volume is the truncated value itself.
+// value Lq (b = Lq + P1) and its minimum (mm, both halves); the byte written to the path volume is the truncated
+// value itself.
 template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ void first_line_step(uint32_t (&Lq)[NR], uint32_t &mm, const uint32_t (&c)[NR], const LaneInfo<LPC> &li,
-                                                bool first_column, uint32_t (&q)[NR])
+__device__ __forceinline__ void first_line_step(uint32_t (&Lq)[NR], uint32_t (&b)[NR], uint32_t &mm, const uint32_t (&c)[NR],
+                                                const LaneInfo<NR, LPC, FULL> &li, bool first_column, uint32_t (&q)[NR])
 {
     if (first_column) {
 #pragma unroll
         for (int k = 0; k < NR; k++) q[k] = c[k];
     } else {
-        uint32_t E[NR + 1];
-        neighbours<NR>(Lq, li.up_mask, li.dn_mask, E);
+        uint32_t left, right;
+        end_neighbours<NR>(b, li.up_mask, li.dn_mask, left, right);
         const uint32_t p2 = mm + kP2x2;
 #pragma unroll
         for (int k = 0; k < NR; k++) {
-            const uint32_t x = __viaddmin_s16x2(E[k], kP1x2, Lq[k]);
-            const uint32_t y = __viaddmin_s16x2(E[k + 1], kP1x2, p2);
-            q[k] = (c[k] + (__vmins2(x, y) - mm)) & 0x00FF00FFu;
+            const uint32_t x = __vimin3_s16x2(Lq[k], k == 0 ? left : b[k - 1], k == NR - 1 ? right : b[k + 1]);
+            q[k] = (c[k] + (__vmins2(x, p2) - mm)) & 0x00FF00FFu;
         }
     }
-    uint32_t m2 = kInf2;
 #pragma unroll
     for (int k = 0; k < NR; k++) {
-        Lq[k] = (FULL || k < li.nvalid) ? q[k] : kInf2;
-        m2 = __vmins2(m2, Lq[k]);
+        Lq[k] = li.padded(q[k], k);
+        b[k] = Lq[k] + kP1x2;
     }
-    mm = chain_min2<LPC>(m2, li.others);
+    mm = chain_min2<LPC>(lane_min<NR>(Lq));
 }
 
-// store the step's penalty bytes (q <= 255 in both halves): 2 * NR bytes per lane
-template <int NR, bool FULL> __device__ __forceinline__ void store_q(uint8_t *dst, const uint32_t (&q)[NR], int nvalid)
+// ---- byte <-> register conversion. A lane's 2NR cost bytes are contiguous in the cell (natural disparity order): 16-bit
+// unit u (u < NR) holds disparities d0 + 2u, d0 + 2u + 1. The "pair word" X[t] = (lo[2t], lo[2t+1], hi[2t], hi[2t+1]) is
+// (unit t, unit NR/2 + t); registers 2t, 2t+1 are its even / odd bytes.
+
+template <int NR> __device__ __forceinline__ void unpack_cost(const uint32_t (&w)[NR / 2], uint32_t (&c)[NR])
 {
-    if constexpr (NR % 2 == 0) {
-        // sl * 2NR is a multiple of 4 (of 8 when NR % 4 == 0) and cell * D a multiple of 8: the stores are aligned
-        if (FULL || nvalid == NR) {
-            uint32_t w[NR / 2];
+    static_assert(NR % 2 == 0, "an even number of packed registers per lane");
 #pragma unroll
-            for (int k = 0; k < NR / 2; k++) w[k] = __byte_perm(q[2 * k], q[2 * k + 1], 0x6420);
-            if constexpr (FULL && NR % 8 == 0) {
+    for (int t = 0; t < NR / 2; t++) {
+        constexpr int H = NR / 2;
+        const int ua = t, ub = H + t; // units
+        const uint32_t sel = ((ub & 1) ? 0x7600u : 0x5400u) | ((ua & 1) ? 0x32u : 0x10u);
+        const uint32_t X = __byte_perm(w[ua >> 1], w[ub >> 1], sel);
+        c[2 * t + 1] = __byte_perm(X, 0u, 0x4341);
+        c[2 * t] = X - (c[2 * t + 1] << 8); // == X & 0x00FF00FF, written so that it can issue as an IMAD on the FMA pipe
+    }
+}
+
+template <int NR> __device__ __forceinline__ void pack_q(const uint32_t (&q)[NR], uint32_t (&w)[NR / 2])
+{
+    uint32_t X[NR / 2];
 #pragma unroll
-                for (int k = 0; k < NR / 8; k++) reinterpret_cast<uint4 *>(dst)[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
-            } else if constexpr (NR % 4 == 0) {
+    for (int t = 0; t < NR / 2; t++) X[t] = q[2 * t + 1] * 256u + q[2 * t];
 #pragma unroll
-                for (int k = 0; k < NR / 4; k++) reinterpret_cast<uint2 *>(dst)[k] = make_uint2(w[2 * k], w[2 * k + 1]);
-            } else {
+    for (int j = 0; j < NR / 2; j++) {
+        constexpr int H = NR / 2;
+        const int u0 = 2 * j, u1 = 2 * j + 1;
+        const uint32_t sel = ((u1 >= H) ? 0x7600u : 0x5400u) | ((u0 >= H) ? 0x32u : 0x10u);
+        w[j] = __byte_perm(X[u0 % H], X[u1 % H], sel);
+    }
+}
+
+// store the step's penalty bytes (q <= 255 in both halves): 2 * NR bytes per lane at dst (the lane's first byte)
+__device__ __forceinline__ void stg32(uint8_t *p, uint32_t x) { asm volatile("st.global.u32 [%0], %1;\n" ::"l"(p), "r"(x) : "memory"); }
+__device__ __forceinline__ void stg64(uint8_t *p, uint32_t x, uint32_t y) { asm volatile("st.global.v2.u32 [%0], {%1, %2};\n" ::"l"(p), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ void stg128(uint8_t *p, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+template <int NR, bool FULL> __device__ __forceinline__ void store_q(uint8_t *dst, const uint32_t (&q)[NR], int valid_bytes)
+{
+    uint32_t w[NR / 2];
+    pack_q<NR>(q, w);
+    if constexpr (FULL && NR % 8 == 0) {
 #pragma unroll
-                for (int k = 0; k < NR / 2; k++) reinterpret_cast<uint32_t *>(dst)[k] = w[k];
-            }
-        } else {
+        for (int k = 0; k < NR / 8; k++) stg128(dst + 16 * k, w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    } else if constexpr (FULL && NR % 4 == 0) {
 #pragma unroll
-            for (int k = 0; k < NR; k++)
-                if (k < nvalid) reinterpret_cast<uint16_t *>(dst)[k] = (uint16_t)__byte_perm(q[k], 0u, 0x4420);
+        for (int k = 0; k < NR / 4; k++) stg64(dst + 8 * k, w[2 * k], w[2 * k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < NR / 2; k++)
+            if (FULL || 4 * k < valid_bytes) stg32(dst + 4 * k, w[k]);
+    }
+}
+
+// ---- cost stream. The fused-cost bytes a chain will need are known in advance: each lane loads its own 2NR bytes of
+// the cell kAhead steps early straight into registers (LDG, L1-cached: the few instructions that cover one cell hit
+// the same lines) and asks L2 for the cell kAhead + kFar steps early (PREFETCH.L2), so no step waits on DRAM or L2.
+#ifndef SISTER_SGM_AHEAD
+#define SISTER_SGM_AHEAD 3
+#endif
+#ifndef SISTER_SGM_FAR
+#define SISTER_SGM_FAR 8
+#endif
+constexpr int kAhead = SISTER_SGM_AHEAD;   // register lookahead, steps (loop unrolled by kAhead, buffers rotate at compile time)
+constexpr int kFar = SISTER_SGM_FAR;       // L2 prefetch distance beyond the register lookahead, steps
+
+__device__ __forceinline__ void prefetch_l2(const uint8_t *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
+template <int NR, bool FULL> __device__ __forceinline__ void load_cost(const uint8_t *src, int valid_bytes, uint32_t (&w)[NR / 2])
+{
+    if constexpr (FULL && NR % 8 == 0) {
+#pragma unroll
+        for (int k = 0; k < NR / 8; k++) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src) + k);
+            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        }
+    } else if constexpr (FULL && NR % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < NR / 4; k++) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src) + k);
+            w[2 * k] = v.x; w[2 * k + 1] = v.y;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < NR; k++)
-            if (FULL || k < nvalid) reinterpret_cast<uint16_t *>(dst)[k] = (uint16_t)__byte_perm(q[k], 0u, 0x4420);
+        for (int k = 0; k < NR / 2; k++) w[k] = (FULL || 4 * k < valid_bytes) ? __ldg(reinterpret_cast<const uint32_t *>(src) + k) : 0u;
     }
 }
-
-// Per-lane view of one chain: cursors are 32-bit offsets in units of 8 bytes (D % 8 == 0) from the volume base, turned
-// into addresses with one IMAD.WIDE; the cost ring is kRing slots of LPC * 2NR bytes per chain.
-template <int NR, int LPC, bool FULL> struct ChainRun {
-    static constexpr int kSlotBytes = LPC * 2 * NR;
-    static constexpr unsigned kRingBytes = kRing * kSlotBytes;
-    // the two chains of a warp read their rings in the same instruction: offset the second ring by 16 banks
-    static constexpr unsigned kChainPitch = kRingBytes + ((kRingBytes % 128 == 0 && LPC < 32) ? 64 : 0);
-    // FULL (D == LPC * 2NR, a multiple of 16): 16-byte copies, LPC * NR / 8 of them per cell; otherwise 8-byte copies
-    static constexpr int kRounds = (NR + 3) / 4;    // 8-byte cp.async rounds: LPC lanes fetch LPC * 8 bytes per round
-    static constexpr int kRounds16 = (NR + 7) / 8;  // 16-byte rounds
-    const uint8_t *fused_lane; // fused + sl * 8 (or sl * 16)
-    uint8_t *q_lane;           // path volume + sl * 2NR
-    unsigned ring_ld;          // shared address of the chain's ring + sl * 2NR (reads)
-    unsigned ring_st;          // shared address of the chain's ring + sl * 8 (or sl * 16): cp.async destination
-    int D, sl;
-    unsigned on16[kRounds16];  // FULL: does this lane copy in round r
-    unsigned rd_off = 0;                           // ring slot of the step being consumed
-    unsigned wr_off = (kRing - 1) * kSlotBytes;    // free slot: the one consumed in the previous step
-
-    __device__ __forceinline__ void issue(unsigned slot_off, int off8) const
-    {
-        const uint8_t *src = fused_lane + (long long)off8 * 8;
-        if constexpr (FULL) {
-#pragma unroll
-            for (int r = 0; r < kRounds16; r++) {
-                if ((r + 1) * LPC * 16 <= LPC * 2 * NR) cp_async16(ring_st + slot_off + r * LPC * 16, src + r * LPC * 16);
-                else cp_async16_if(ring_st + slot_off + r * LPC * 16, src + r * LPC * 16, on16[r]);
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < kRounds; r++)
-                if ((sl + r * LPC) * 8 < D) cp_async8(ring_st + slot_off + r * LPC * 8, src + r * LPC * 8);
-        }
-    }
-    __device__ __forceinline__ void consume(uint32_t (&c)[NR]) const
-    {
-        cp_async_wait<kRing - 2>();
-        __syncwarp();
-        const unsigned src = ring_ld + rd_off;
-        if constexpr (NR % 4 == 0) {
-#pragma unroll
-            for (int k = 0; k < NR / 4; k++) {
-                uint32_t v0, v1;
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v0), "=r"(v1) : "r"(src + 8 * k) : "memory");
-                c[4 * k] = __byte_perm(v0, 0u, 0x4140);
-                c[4 * k + 1] = __byte_perm(v0, 0u, 0x4342);
-                c[4 * k + 2] = __byte_perm(v1, 0u, 0x4140);
-                c[4 * k + 3] = __byte_perm(v1, 0u, 0x4342);
-            }
-        } else if constexpr (NR % 2 == 0) {
-#pragma unroll
-            for (int k = 0; k < NR / 2; k++) {
-                uint32_t v;
-                asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(src + 4 * k) : "memory");
-                c[2 * k] = __byte_perm(v, 0u, 0x4140);
-                c[2 * k + 1] = __byte_perm(v, 0u, 0x4342);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < NR; k++) {
-                unsigned short v;
-                asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(src + 2 * k) : "memory");
-                c[k] = __byte_perm((uint32_t)v, 0u, 0x4140);
-            }
-        }
-    }
-    // returns the free slot (consumed one step ago, every lane is past its reads: a __syncwarp lies in between),
-    // frees the slot consumed in this step for the next one and moves on
-    __device__ __forceinline__ unsigned advance_ring()
-    {
-        const unsigned free_slot = wr_off;
-        wr_off = rd_off;
-        rd_off = (rd_off + kSlotBytes == kRingBytes) ? 0u : rd_off + kSlotBytes;
-        return free_slot;
-    }
-};
 
 } // namespace sister
