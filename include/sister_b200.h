@@ -74,7 +74,8 @@ int sister_destroy(sister_ctx *ctx);
  *   out         3 pointers (multiview, horizontal, vertical), each H x W uint16, dense; entries whose
  *               mode bit is clear may be NULL and are not touched
  *   raw_disp    optional: 3 x (h+2D) x (w+2D) int16, the un-encoded integer disparity of the whole
- *               padded frame per mode (what WTALeft_SSE wrote at hpp:283)
+ *               padded frame per mode (what WTALeft_SSE wrote at hpp:283). Asking for it makes this call
+ *               aggregate the whole padded frame (see sister_set_full_frame).
  */
 int sister_compute(sister_ctx *ctx, const uint8_t *const views[5], int w, int h, int channels,
                    size_t row_stride, int disp_count, unsigned mode_mask, uint16_t *const out[3],
@@ -98,6 +99,16 @@ int sister_wait(sister_ctx *ctx, int slot, uint16_t *const out[3], int16_t *raw_
 int sister_submit_device(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h,
                          int channels, int disp_count, unsigned mode_mask, uint16_t *const out_dev[3]);
 int sister_sync(sister_ctx *ctx, int slot); /* slot < 0: all slots */
+
+/* compute_disparities returns the crop Rect(D, D, W, H) of each map (hpp:116-118), and nothing else of the
+ * padded frame ever leaves the reference. By default the aggregation therefore runs for that crop only: SGM
+ * paths still start at the borders of the padded frame (their state flows into the crop exactly as in
+ * sgm.cpp:26-455), but paths that never reach the crop are skipped, the others stop once they have left it,
+ * and the aggregated cost is formed inside it only. The three output maps are bit-identical either way.
+ * enabled = 1 aggregates the whole padded frame on later submits, which the raw_disp argument of
+ * sister_wait and SISTER_TAP_RAW_DISP / SISTER_TAP_SUM need (sister_compute with raw_disp and
+ * sister_set_test_taps switch it on by themselves). */
+int sister_set_full_frame(sister_ctx *ctx, int enabled);
 
 /* Plain device memory helpers so that a host language needs no CUDA binding of its own. */
 int sister_dev_alloc(sister_ctx *ctx, size_t bytes, void **dev_ptr);

@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "sister_create", "sister_destroy", "sister_compute", "sister_compute_batch", "sister_submit", "sister_wait",
     "sister_submit_device", "sister_sync", "sister_dev_alloc", "sister_dev_free", "sister_host_alloc", "sister_host_free", "sister_dev_upload",
     "sister_dev_download", "sister_set_profiling", "sister_region_begin", "sister_region_end", "sister_get_stage_ms", "sister_get_stage_launches",
-    "sister_get_launch_count", "sister_debug_fetch", "sister_set_test_taps", "sister_test_sgm", "sister_strerror", "sister_last_error",
+    "sister_get_launch_count", "sister_debug_fetch", "sister_set_test_taps", "sister_set_full_frame", "sister_test_sgm", "sister_strerror", "sister_last_error",
     "sister_version",
 )
 
@@ -102,6 +102,8 @@ def load_library():
     L.sister_debug_fetch.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t]
     L.sister_set_test_taps.restype = C.c_int
     L.sister_set_test_taps.argtypes = [vp, C.c_int]
+    L.sister_set_full_frame.restype = C.c_int
+    L.sister_set_full_frame.argtypes = [vp, C.c_int]
     L.sister_test_sgm.restype = C.c_int
     L.sister_test_sgm.argtypes = [vp, _u8p, C.c_int, C.c_int, C.c_int, _u16p, _i16p]
     L.sister_strerror.restype = C.c_char_p
@@ -253,6 +255,10 @@ class Engine:
     def set_test_taps(self, on: bool):
         """Keep the aggregated volume of later submits for fetch("sum", ...) (tests only; 2 * cells bytes per slot)."""
         self._chk(self.lib.sister_set_test_taps(self.ctx, int(on)))
+
+    def set_full_frame(self, on: bool):
+        """Aggregate the whole padded frame on later submits instead of the crop the caller sees (needed for raw_disp)."""
+        self._chk(self.lib.sister_set_full_frame(self.ctx, int(on)))
 
     def region_begin(self):
         self._chk(self.lib.sister_region_begin(self.ctx))

@@ -33,6 +33,7 @@ struct Slot {
     Dims dims{};
     unsigned mode_mask = 0;
     bool busy = false, host_io = false;
+    bool full_frame = false; // the last run aggregated the whole padded frame (raw_disp is complete)
     // profiling
     std::vector<cudaEvent_t> ev_b, ev_e;
     std::vector<int> ev_stage;
@@ -50,6 +51,7 @@ struct sister_ctx {
     std::vector<Slot> slots;
     bool profiling = false;
     bool taps = false; // keep the aggregated volume for SISTER_TAP_SUM (tests only)
+    bool full_frame = false; // aggregate the whole padded frame (raw_disp, taps) instead of the crop the caller sees
     cudaEvent_t region_b = nullptr, region_e = nullptr;
     std::vector<cudaEvent_t> region_join;
     LaunchCounter lc;
@@ -144,7 +146,7 @@ int run_pipeline(sister_ctx *ctx, Slot &s, const uint8_t *const in_views[5], int
         launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused, s.d_status, s.st, ctx->lc);
         end_stage(ctx, s);
         begin_stage(ctx, s, SISTER_STAGE_AGGREGATE);
-        launch_sgm(s.d_fused, d, s.d_paths, ctx->taps ? s.d_sum : nullptr, s.d_raw + (size_t)mode * d.px,
+        launch_sgm(s.d_fused, d, ctx->full_frame || ctx->taps, s.d_paths, ctx->taps ? s.d_sum : nullptr, s.d_raw + (size_t)mode * d.px,
                    out_dev ? out_dev[mode] : nullptr, s.d_status, s.st, ctx->lc);
         end_stage(ctx, s);
     }
@@ -153,6 +155,7 @@ int run_pipeline(sister_ctx *ctx, Slot &s, const uint8_t *const in_views[5], int
     for (int k = 0; k < SISTER_STAGE_COUNT; k++) s.stage_launches[k] = ctx->lc.stage[k] - before[k];
     s.dims = d;
     s.mode_mask = mode_mask;
+    s.full_frame = ctx->full_frame || ctx->taps;
     return SISTER_OK;
 }
 
@@ -322,14 +325,21 @@ int sister_wait(sister_ctx *ctx, int slot, uint16_t *const out[3], int16_t *raw_
     const size_t wh = (size_t)s.dims.W * s.dims.H;
     for (int m = 0; m < 3; m++)
         if ((s.mode_mask & (1u << m)) && out && out[m]) memcpy(out[m], s.h_out + m * wh, wh * 2);
-    if (raw_disp) SCK(cudaMemcpy(raw_disp, s.d_raw, (size_t)3 * s.dims.px * 2, cudaMemcpyDeviceToHost));
+    if (raw_disp) {
+        if (!s.full_frame) { ctx->err = "raw_disp needs sister_set_full_frame(ctx, 1) before the submit"; return SISTER_E_ARG; }
+        SCK(cudaMemcpy(raw_disp, s.d_raw, (size_t)3 * s.dims.px * 2, cudaMemcpyDeviceToHost));
+    }
     return SISTER_OK;
 }
 
 int sister_compute(sister_ctx *ctx, const uint8_t *const views[5], int w, int h, int channels, size_t row_stride,
                    int disp_count, unsigned mode_mask, uint16_t *const out[3], int16_t *raw_disp)
 {
+    if (!ctx) return SISTER_E_ARG;
+    const bool keep = ctx->full_frame;
+    if (raw_disp) ctx->full_frame = true; // the whole padded map is asked for: aggregate the whole frame
     int rc = sister_submit(ctx, 0, views, w, h, channels, row_stride, disp_count, mode_mask);
+    ctx->full_frame = keep;
     if (rc) return rc;
     return sister_wait(ctx, 0, out, raw_disp);
 }
@@ -433,6 +443,13 @@ int sister_dev_download(sister_ctx *ctx, void *host_dst, const void *dev_src, si
     return SISTER_OK;
 }
 
+int sister_set_full_frame(sister_ctx *ctx, int enabled)
+{
+    if (!ctx) return SISTER_E_ARG;
+    ctx->full_frame = enabled != 0;
+    return SISTER_OK;
+}
+
 int sister_set_test_taps(sister_ctx *ctx, int enabled)
 {
     if (!ctx) return SISTER_E_ARG;
@@ -533,7 +550,9 @@ int sister_debug_fetch(sister_ctx *ctx, int slot, int what, void *host_dst, size
     case SISTER_TAP_SUM:
         if (!ctx->taps || !s.d_sum) { ctx->err = "SISTER_TAP_SUM needs sister_set_test_taps(ctx, 1) before the submit"; return SISTER_E_ARG; }
         src = s.d_sum; have = cells * 2; break;
-    case SISTER_TAP_RAW_DISP: src = s.d_raw; have = 3 * px * 2; break;
+    case SISTER_TAP_RAW_DISP:
+        if (!s.full_frame) { ctx->err = "SISTER_TAP_RAW_DISP needs sister_set_full_frame(ctx, 1) or the test taps before the submit"; return SISTER_E_ARG; }
+        src = s.d_raw; have = 3 * px * 2; break;
     default: ctx->err = "unknown tap"; return SISTER_E_ARG;
     }
     if (bytes > have) { ctx->err = "tap smaller than requested"; return SISTER_E_ARG; }
@@ -557,7 +576,7 @@ int sister_test_sgm(sister_ctx *ctx, const uint8_t *fused, int w, int h, int dis
     SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
     if (!s.d_sum) SCK(cudaMalloc((void **)&s.d_sum, (size_t)ctx->cells_max * 2));
     ctx->lc.cur_stage = SISTER_STAGE_AGGREGATE;
-    launch_sgm(s.d_fused, d, s.d_paths, s.d_sum, s.d_raw, nullptr, s.d_status, s.st, ctx->lc);
+    launch_sgm(s.d_fused, d, true, s.d_paths, s.d_sum, s.d_raw, nullptr, s.d_status, s.st, ctx->lc);
     SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
     SCK(cudaGetLastError());
     SCK(cudaStreamSynchronize(s.st));

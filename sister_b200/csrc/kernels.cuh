@@ -33,7 +33,10 @@ void launch_fuse(const unsigned long long *census, const uint8_t *masks, const D
 // 8-path SGM (sgm.cpp:26-455) on the uint8 fused volume: 8 one-byte path volumes (qvol, 8 * cells bytes), then
 // S = nC * C + sum of the path bytes, the final WTA-left (hpp:283) and convertTo/crop/*255 (hpp:111-118) in one sweep.
 // sum (uint16 [Hp][Wp][D]) is written only when non-null (test tap); raw_disp / out may be null.
-void launch_sgm(const uint8_t *fused, const Dims &d, uint8_t *qvol, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
+// full_frame = false aggregates for the crop Rect(D, D, W, H) only (all the caller ever sees, hpp:116-118): chains that
+// never reach it are skipped, the others stop once they have left it, path bytes exist only inside it. raw_disp and sum
+// are then written inside the crop only.
+void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, uint8_t *qvol, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
                 int *status, cudaStream_t st, LaunchCounter &lc);
 
 } // namespace sister

@@ -48,76 +48,112 @@ struct Chain {
     int vol;        // path volume index: 4 * pass + path
 };
 
-// Chain numbering, three sections, each padded to a multiple of `cpw` (chains per warp) so that a warp never mixes
-// kinds; a padding slot repeats the section's last chain (it recomputes and rewrites the same bytes):
-//   kind 1  [2]              r0 on the first line of pass 0 / pass 1
-//   kind 0  [2 * (Hp-1)]     r0 on the other rows
-//   kind 2  [6 * Wp]         r1, r2, r3 of a pass, ordered [pass][path][column]: the chains of a warp sit on adjacent
-//                            columns of the same row, so a step reads and writes one contiguous run of cells; the three
-//                            paths of a pass start together and advance at the same rate, so every row of C is read
-//                            three times within a short window -- two of the three reads hit L2
-struct Sections {
-    long long n[3], o[4];
+// Region of interest: the cells whose aggregated cost is consumed. The caller only ever sees the crop
+// Rect(D, D, W, H) of the disparity map (hpp:116-118), so outside of test / raw-disparity runs the path bytes are
+// needed there and nowhere else. SGM state still flows in from the borders of the padded frame, so a chain starts
+// where it always did, but
+//   * a chain that never touches the region is not run (rows above / below it, columns left / right of it);
+//   * a chain stops once it has left the region for good (its remaining cells feed nothing);
+//   * path bytes are stored, and summed by k_sgm_final, inside the region only.
+// The full frame (r0 = c0 = 0, r1 = Hp, c1 = Wp) reproduces the reference's whole aggregated volume.
+struct Roi {
+    int r0, r1, c0, c1;
 };
-__host__ __device__ inline Sections chain_sections(const Dims &d, int cpw)
+__host__ __device__ inline bool roi_is_full(const Roi &r, const Dims &d) { return r.r0 == 0 && r.c0 == 0 && r.r1 == d.Hp && r.c1 == d.Wp; }
+
+// Chain numbering: nine sections, each padded to a multiple of `cpw` (chains per warp) so that a warp never mixes
+// sections; a padding slot repeats the section's last chain (it recomputes and rewrites the same bytes):
+//   0        kind 1   r0 on the first line of pass 0 / pass 1 (rows 0 and Hp-1; only when the region contains them)
+//   1, 2     kind 0   r0 of pass 0 / pass 1 on the other rows of the region
+//   3 .. 8   kind 2   [pass][path r1, r2, r3][column]: the chains of a warp sit on adjacent columns of the same row, so
+//                     a step reads and writes one contiguous run of cells; the three paths of a pass start together
+//                     and advance at the same rate, so every row of C is read three times within a short window and
+//                     two of the three reads hit L2. r2 runs on the region's columns only, the diagonals on all.
+struct Sections {
+    int n[9], lo[9];   // chains in the section, first row / column
+    long long o[10];   // first chain index (padded)
+};
+inline Sections chain_sections(const Dims &d, const Roi &r, int cpw)
 {
     Sections s;
-    const long long cnt[3] = {2, 2LL * (d.Hp - 1), 6LL * d.Wp};
+    const bool first = r.r0 == 0, last = r.r1 == d.Hp;
+    s.n[0] = (first ? 1 : 0) + (last ? 1 : 0);
+    s.lo[0] = first ? 0 : 1; // pass of the section's first chain
+    s.lo[1] = r.r0 > 1 ? r.r0 : 1;                        // pass 0: row 0 is the first line
+    s.n[1] = r.r1 - s.lo[1];
+    s.lo[2] = r.r0;                                       // pass 1: row Hp-1 is the first line
+    s.n[2] = (r.r1 < d.Hp - 1 ? r.r1 : d.Hp - 1) - r.r0;
+    for (int p = 0; p < 2; p++)
+        for (int t = 0; t < 3; t++) {
+            s.lo[3 + 3 * p + t] = t == 1 ? r.c0 : 0;
+            s.n[3 + 3 * p + t] = t == 1 ? r.c1 - r.c0 : d.Wp;
+        }
     s.o[0] = 0;
-    for (int k = 0; k < 3; k++) {
-        s.n[k] = cnt[k];
-        s.o[k + 1] = s.o[k] + (cnt[k] + cpw - 1) / cpw * cpw;
+    for (int k = 0; k < 9; k++) {
+        if (s.n[k] < 0) s.n[k] = 0;
+        s.o[k + 1] = s.o[k] + ((long long)s.n[k] + cpw - 1) / cpw * cpw;
     }
     return s;
 }
 
 // returns the kind (0..2) or -1 when g is past the end
-__device__ __forceinline__ int chain_decode(const Dims &d, const Sections &sec, long long g, Chain &ch, int &nsteps)
+__device__ __forceinline__ int chain_decode(const Dims &d, const Roi &r, const Sections &sec, long long g, Chain &ch, int &nsteps)
 {
-    if (g >= sec.o[3]) return -1;
-    if (g < sec.o[1]) {
-        const int p = (int)min(g, sec.n[0] - 1);
+    if (g >= sec.o[9]) return -1;
+    int k = 0;
+#pragma unroll
+    for (int q = 1; q < 9; q++) k += g >= sec.o[q];
+    const int idx = (int)min(g - sec.o[k], (long long)sec.n[k] - 1);
+    if (k == 0) {
+        const int p = sec.lo[0] + idx;
         ch.i = p ? d.Hp - 1 : 0; ch.j = p ? d.Wp - 1 : 0; ch.si = 0; ch.sj = p ? -1 : 1; ch.enter = 0;
-        ch.vol = 4 * p; nsteps = d.Wp;
+        ch.vol = 4 * p; nsteps = p ? d.Wp - r.c0 : r.c1;
         return 1;
     }
-    if (g < sec.o[2]) {
-        const long long idx = min(g - sec.o[1], sec.n[1] - 1);
-        const int p = (int)(idx / (d.Hp - 1)), r = (int)(idx % (d.Hp - 1));
-        ch.i = p ? r : r + 1; ch.j = p ? d.Wp - 1 : 0; ch.si = 0; ch.sj = p ? -1 : 1; ch.enter = 0;
-        ch.vol = 4 * p; nsteps = d.Wp;
+    if (k < 3) {
+        const int p = k - 1;
+        ch.i = sec.lo[k] + idx; ch.j = p ? d.Wp - 1 : 0; ch.si = 0; ch.sj = p ? -1 : 1; ch.enter = 0;
+        ch.vol = 4 * p; nsteps = p ? d.Wp - r.c0 : r.c1;
         return 0;
     }
-    const long long idx = min(g - sec.o[2], sec.n[2] - 1);
-    const int p = (int)(idx / (3LL * d.Wp));
-    const int rem = (int)(idx % (3LL * d.Wp)), type = rem / d.Wp, col = rem % d.Wp; // 0: r1, 1: r2, 2: r3
+    const int p = (k - 3) / 3, type = (k - 3) % 3; // 0: r1, 1: r2, 2: r3
     const int dj = p ? -1 : 1, j1 = p ? d.Wp - 1 : 0, jl = p ? 0 : d.Wp - 1;
-    ch.i = p ? d.Hp - 1 : 0; ch.j = col; ch.si = dj;
+    ch.i = p ? d.Hp - 1 : 0; ch.j = sec.lo[k] + idx; ch.si = dj;
     ch.sj = type == 0 ? dj : type == 1 ? 0 : -dj;
     ch.enter = type == 0 ? j1 : jl; // unused by r2 (sj = 0 never leaves the frame)
-    ch.vol = 4 * p + 1 + type; nsteps = d.Hp;
+    ch.vol = 4 * p + 1 + type; nsteps = p ? d.Hp - r.r0 : r.r1;
     return 2;
 }
 
 // ---------------------------------------------------------------------------------------------- the path kernel
 
-// Cursor of a chain: 32-bit offset in units of 8 bytes (D % 8 == 0) from the volume base plus the column, which a
-// diagonal chain needs to notice that it stepped over a side border; it then re-enters at the opposite border of the
-// same row (a fixed correction of one row of cells).
+// Cursor of a chain: 32-bit offset in units of 8 bytes (D % 8 == 0) from the volume base plus the cell's row and
+// column: a diagonal chain needs the column to notice that it stepped over a side border (it then re-enters at the
+// opposite border of the same row, a fixed correction of one row of cells), the store cursor needs both to know
+// whether the cell lies in the region of interest.
 struct Cursor {
-    int off8, j;
+    int off8, i, j;
 };
 struct Walk {
-    int stride8, wrapfix8, sj, enter, Wp;
+    int stride8, wrapfix8, si, sj, enter, Wp;
+    int r0, c0;            // region of interest ...
+    unsigned nr, nc;       // ... and its height / width
 };
 template <bool DIAG> __device__ __forceinline__ bool advance(Cursor &c, const Walk &w)
 {
     c.off8 += w.stride8;
+    c.j += w.sj;
     if constexpr (DIAG) {
-        c.j += w.sj;
+        c.i += w.si;
         if ((unsigned)c.j >= (unsigned)w.Wp) { c.j = w.enter; c.off8 += w.wrapfix8; return true; }
     }
     return false;
+}
+template <bool DIAG> __device__ __forceinline__ bool in_roi(const Cursor &c, const Walk &w)
+{
+    const bool col = (unsigned)(c.j - w.c0) < w.nc;
+    if constexpr (DIAG) return col && (unsigned)(c.i - w.r0) < w.nr;
+    else return col; // a row chain only runs on rows of the region
 }
 
 // KIND 0: r0 on an ordinary row; 1: r0 on the first line of a pass; 2: r1 / r2 / r3 (columns ride along in the
@@ -160,6 +196,7 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
             advance<DIAG>(pf, wk);
         }
         uint8_t *dst = q_lane + (long long)st.off8 * 8;
+        const bool wanted = in_roi<DIAG>(st, wk);
         const bool off_next = advance<DIAG>(st, wk); // KIND 2: the next cell follows a border crossing
         if constexpr (KIND == 1) {
             first_line_step<NR, LPC, FULL>(cs.a, cs.b, mm, c, li, s == 0, q);
@@ -168,7 +205,7 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
         } else {
             chain_step<NR, LPC, FULL>(cs, c, li, q, off_next);
         }
-        store_q<NR, FULL>(dst, q, valid_bytes);
+        if (wanted) store_q<NR, FULL>(dst, q, valid_bytes);
     };
     int s0 = 0;
 #pragma unroll 1
@@ -183,16 +220,15 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
 
 // grid ceil(chains / (kChainWarps * 32 / LPC)), block kChainWarps * 32, no shared memory
 template <int NR, int LPC, bool FULL>
-__global__ void __launch_bounds__(kChainWarps * 32, ((NR <= 8 || (FULL && NR <= 12)) ? 24 : 16) / kChainWarps) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, uint8_t *__restrict__ qvol, unsigned kind_mask)
+__global__ void __launch_bounds__(kChainWarps * 32, ((NR <= 8 || (FULL && NR <= 12)) ? 24 : 16) / kChainWarps) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, Roi roi, Sections sec, uint8_t *__restrict__ qvol, unsigned kind_mask)
 {
     constexpr int CPW = 32 / LPC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     LaneInfo<NR, LPC, FULL> li;
     li.init(lane, d.D);
-    const Sections sec = chain_sections(d, CPW);
     Chain ch;
     int nsteps = 0;
-    const int kind = chain_decode(d, sec, ((long long)blockIdx.x * kChainWarps + warp) * CPW + lane / LPC, ch, nsteps);
+    const int kind = chain_decode(d, roi, sec, ((long long)blockIdx.x * kChainWarps + warp) * CPW + lane / LPC, ch, nsteps);
     if (kind < 0) return; // warp-uniform: sections are padded to whole warps
     if (!((kind_mask >> kind) & 1u)) return; // measurement aid (SISTER_DEBUG_PATH_KINDS), always 7 in the product
     const int D = d.D, Wp = d.Wp, D8 = D >> 3;
@@ -205,9 +241,11 @@ __global__ void __launch_bounds__(kChainWarps * 32, ((NR <= 8 || (FULL && NR <= 
     Walk wk;
     wk.stride8 = (ch.si * Wp + ch.sj) * D8;
     wk.wrapfix8 = -ch.sj * Wp * D8;
-    wk.sj = ch.sj; wk.enter = ch.enter; wk.Wp = Wp;
+    wk.si = ch.si; wk.sj = ch.sj; wk.enter = ch.enter; wk.Wp = Wp;
+    wk.r0 = roi.r0; wk.c0 = roi.c0; wk.nr = (unsigned)(roi.r1 - roi.r0); wk.nc = (unsigned)(roi.c1 - roi.c0);
     Cursor first;
     first.off8 = (ch.i * Wp + ch.j) * D8;
+    first.i = ch.i;
     first.j = ch.j;
     if (kind == 1) run_chain<NR, LPC, FULL, 1>(fused_lane, q_lane, li, wk, first, nsteps, valid_bytes);
     else if (kind == 0) run_chain<NR, LPC, FULL, 0>(fused_lane, q_lane, li, wk, first, nsteps, valid_bytes);
@@ -222,7 +260,7 @@ __device__ __forceinline__ uint2 ldg8(const uint8_t *p) { return __ldg(reinterpr
 // convertTo(CV_16UC1), crop Rect(D, D, W, H) and * 255 with saturation (hpp:111-118).
 // Eight lanes per pixel, each lane owns 8-byte chunks sub, sub + 8, ... of the pixel's D bytes in all nine volumes.
 // grid-stride over groups of 4 pixels per warp.
-__global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ fused, const uint8_t *__restrict__ qvol, Dims d,
+__global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ fused, const uint8_t *__restrict__ qvol, Dims d, Roi roi,
                                                    uint16_t *__restrict__ sum, int16_t *__restrict__ raw_disp, uint16_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
@@ -230,10 +268,13 @@ __global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ f
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const int D = d.D, nchunk = D >> 3;
     const size_t cells = (size_t)d.cells;
-    for (long long base = warp0 * 4; base < d.px; base += nwarps * 4) {
-        const long long pix = base + grp;
-        const bool live = pix < d.px;
-        const int i = live ? (int)(pix / d.Wp) : 0, j = live ? (int)(pix % d.Wp) : 0;
+    const int wroi = roi.c1 - roi.c0;
+    const long long npx = (long long)(roi.r1 - roi.r0) * wroi; // pixels of the region of interest, row-major
+    for (long long base = warp0 * 4; base < npx; base += nwarps * 4) {
+        const long long t = base + grp;
+        const bool live = t < npx;
+        const int i = live ? roi.r0 + (int)(t / wroi) : 0, j = live ? roi.c0 + (int)(t % wroi) : 0;
+        const long long pix = (long long)i * d.Wp + j;
         const int dmax = min(j, D - 1);
         const int sh = (i == 0 || i == d.Hp - 1) ? 2 : 3; // nC = 4 on the first line of either pass, else 8
         unsigned best = 0xFFFFFFFFu;
@@ -291,16 +332,17 @@ static unsigned path_kind_mask()
 }
 
 template <int NR, int LPC, bool FULL>
-static void launch_paths(const uint8_t *fused, const Dims &d, uint8_t *qvol, cudaStream_t st)
+static void launch_paths(const uint8_t *fused, const Dims &d, const Roi &roi, uint8_t *qvol, cudaStream_t st)
 {
     constexpr int CPW = 32 / LPC;
-    const long long n = chain_sections(d, CPW).o[3];
+    const Sections sec = chain_sections(d, roi, CPW);
+    const long long n = sec.o[9];
     const long long per_block = (long long)kChainWarps * CPW;
-    k_sgm_paths<NR, LPC, FULL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, 0, st>>>(fused, d, qvol, path_kind_mask());
+    k_sgm_paths<NR, LPC, FULL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, 0, st>>>(fused, d, roi, sec, qvol, path_kind_mask());
 }
 
 template <int LPC, int NRMAX>
-static void launch_paths_lpc(const uint8_t *fused, const Dims &d, uint8_t *qvol, cudaStream_t st)
+static void launch_paths_lpc(const uint8_t *fused, const Dims &d, const Roi &roi, uint8_t *qvol, cudaStream_t st)
 {
     // disparities per lane = 2 * NR, NR even, chosen so that D fits in LPC lanes
     const int nr = 2 * ((d.D + 4 * LPC - 1) / (4 * LPC));
@@ -308,8 +350,8 @@ static void launch_paths_lpc(const uint8_t *fused, const Dims &d, uint8_t *qvol,
 #define SISTER_PATHS_CASE(N)                                                                    \
     case N:                                                                                     \
         if constexpr (N <= NRMAX) {                                                             \
-            if (full) launch_paths<N, LPC, true>(fused, d, qvol, st);                           \
-            else launch_paths<N, LPC, false>(fused, d, qvol, st);                               \
+            if (full) launch_paths<N, LPC, true>(fused, d, roi, qvol, st);                           \
+            else launch_paths<N, LPC, false>(fused, d, roi, qvol, st);                               \
         }                                                                                       \
         break;
     switch (nr) {
@@ -319,19 +361,22 @@ static void launch_paths_lpc(const uint8_t *fused, const Dims &d, uint8_t *qvol,
 #undef SISTER_PATHS_CASE
 }
 
-void launch_sgm(const uint8_t *fused, const Dims &d, uint8_t *qvol, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
+void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, uint8_t *qvol, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
                 int *status, cudaStream_t st, LaunchCounter &lc)
 {
     (void)status;
+    Roi roi;
+    if (full_frame) { roi.r0 = 0; roi.r1 = d.Hp; roi.c0 = 0; roi.c1 = d.Wp; }
+    else { roi.r0 = d.D; roi.r1 = d.D + d.H; roi.c0 = d.D; roi.c1 = d.D + d.W; } // Rect(D, D, W, H), hpp:116-118
     // The kernel is bound by DRAM (scattered 192-byte cells, reads and writes mixed), not by issue slots: measured on
     // B200 at D = 192 two chains per warp (twice the warps) and four chains per warp run within 4 % of each other.
-    if (d.D <= 128) launch_paths_lpc<8, 8>(fused, d, qvol, st);         // four chains per warp
-    else launch_paths_lpc<16, 16>(fused, d, qvol, st);                  // two chains per warp (D <= 512, check_shape)
+    if (d.D <= 128) launch_paths_lpc<8, 8>(fused, d, roi, qvol, st);         // four chains per warp
+    else launch_paths_lpc<16, 16>(fused, d, roi, qvol, st);                  // two chains per warp (D <= 512, check_shape)
     lc.add();
-    const long long groups = (d.px + 3) / 4;
+    const long long groups = ((long long)(roi.r1 - roi.r0) * (roi.c1 - roi.c0) + 3) / 4;
     long long blocks = (groups + 7) / 8;
     if (blocks > 148LL * 64) blocks = 148LL * 64;
-    k_sgm_final<<<(unsigned)blocks, 256, 0, st>>>(fused, qvol, d, sum, raw_disp, out);
+    k_sgm_final<<<(unsigned)blocks, 256, 0, st>>>(fused, qvol, d, roi, sum, raw_disp, out);
     lc.add();
 }
 

@@ -135,6 +135,42 @@ def test_config1_against_oracle(oracle_lib):
     assert (outs[0] == ref[0]).all()
 
 
+@pytest.mark.parametrize("name", golden_rigs())
+def test_crop_only_aggregation_reproduces_golden_maps(name):
+    """The product path aggregates for the crop Rect(D, D, W, H) only (sister_set_full_frame): the three maps must be
+    the reference's, and asking for the raw padded map must switch the whole frame back on for that call."""
+    import sister_b200
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    w, h, D = int(g["w"]), int(g["h"]), int(g["D"])
+    views = make_rig(w, h, D, seed=int(g["seed"]), kind=str(g["kind"]), channels=3)
+    with sister_b200.Engine(w, h, D, n_slots=2) as eng:  # no taps: crop only
+        outs = eng.compute(views, D)
+        assert (outs[0] == g["disp_mv"]).all() and (outs[1] == g["disp_h"]).all() and (outs[2] == g["disp_v"]).all()
+        batch = eng.compute_batch([views, views, views], D, mode_mask=5)
+        for r in batch:
+            assert (r[0] == g["disp_mv"]).all() and (r[2] == g["disp_v"]).all()
+        outs2, raw = eng.compute(views, D, want_raw=True)
+        for m in range(3):
+            assert (raw[m] == g[f"raw_disp_m{m}"]).all()
+        for m in range(3):
+            assert (outs2[m] == outs[m]).all()
+
+
+@pytest.mark.parametrize("w,h,D,seed", [(100, 76, 40, 5), (52, 88, 136, 6), (1280, 960, 192, 8), (640, 480, 128, 9), (320, 240, 256, 10)])
+def test_crop_only_equals_full_frame(w, h, D, seed):
+    """Same maps with and without the crop restriction, at shapes where chains are cut short on every side; includes
+    BASELINE.json configs[1] (1280 x 960, D = 192)."""
+    import sister_b200
+    views = make_rig(w, h, D, seed=seed, channels=1)
+    with sister_b200.Engine(w, h, D, n_slots=1) as eng:
+        crop = eng.compute(views, D, mode_mask=3 if max(w, h) > 1000 else 7)
+        eng.set_full_frame(True)
+        full = eng.compute(views, D, mode_mask=3 if max(w, h) > 1000 else 7)
+    for a, b in zip(crop, full):
+        if a is not None:
+            assert (a == b).all(), f"{(a != b).sum()} pixels differ"
+
+
 def test_full_size_properties():
     """BASELINE.json configs[1] shape (1280x960, D = 192): properties that need no CPU oracle."""
     import sister_b200
