@@ -370,7 +370,9 @@ void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, uint8_t *q
     else { roi.r0 = d.D; roi.r1 = d.D + d.H; roi.c0 = d.D; roi.c1 = d.D + d.W; } // Rect(D, D, W, H), hpp:116-118
     // The kernel is bound by DRAM (scattered 192-byte cells, reads and writes mixed), not by issue slots: measured on
     // B200 at D = 192 two chains per warp (twice the warps) and four chains per warp run within 4 % of each other.
-    if (d.D <= 128) launch_paths_lpc<8, 8>(fused, d, roi, qvol, st);         // four chains per warp
+    static int lpc8_max = -1; // measurement aid: SISTER_DEBUG_LPC8_MAXD=<largest D that runs four chains per warp>
+    if (lpc8_max < 0) { const char *e = getenv("SISTER_DEBUG_LPC8_MAXD"); lpc8_max = e ? atoi(e) : 128; }
+    if (d.D <= lpc8_max && d.D <= 192) launch_paths_lpc<8, 12>(fused, d, roi, qvol, st);         // four chains per warp
     else launch_paths_lpc<16, 16>(fused, d, roi, qvol, st);                  // two chains per warp (D <= 512, check_shape)
     lc.add();
     const long long groups = ((long long)(roi.r1 - roi.r0) * (roi.c1 - roi.c0) + 3) / 4;
