@@ -110,6 +110,36 @@ int sister_sync(sister_ctx *ctx, int slot); /* slot < 0: all slots */
  * sister_set_test_taps switch it on by themselves). */
 int sister_set_full_frame(sister_ctx *ctx, int enabled);
 
+/*
+ * Row bands: ONE large frame split over several GPUs (BASELINE.json configs[3]).
+ * Each GPU (one context per GPU, one process per GPU) owns the rows [band_row0, band_row1) of the PADDED frame
+ * (0 .. h + 2 * disp_count). What is split is everything that is a volume: the fused cost (hpp:255-277), the
+ * eight SGM path volumes and the final sum / WTA (sgm.cpp:26-455, hpp:283) -- all of the memory and most of the
+ * time. Staging, census, raw-cost WTA and the masks are computed for the whole frame by every band (their
+ * neighbourhoods reach D rows across a band border for the vertical views, and the recursive median
+ * (postprocess.cpp:15-71 in place) is a whole-map recurrence).
+ * The row paths of SGM are local to a band. A column or diagonal path crosses the bands: pass 0 runs top to
+ * bottom, pass 1 bottom to top, and a band continues each path from the state the neighbouring band left --
+ * the exact recurrence, no approximate overlap. That state is sister_band_state_bytes() of device memory per
+ * pass; moving it between the GPUs (NCCL send / recv, cudaMemcpyPeer) is the caller's job, see
+ * sister_b200/bands.py for the schedule (pass 0 flows down the ranks while pass 1 flows up).
+ *
+ *   sister_band_submit    staging .. masks for the whole frame, fused cost and row paths for the band; mode: 0
+ *                         multiview, 1 horizontal, 2 vertical (one map per call)
+ *   sister_band_vertical  the column / diagonal paths of one pass inside the band. state_in_dev: what the band
+ *                         above (pass 0) / below (pass 1) wrote, NULL on the first band of the pass;
+ *                         state_out_dev: receives the state for the next band, NULL on the last band
+ *   sister_band_finish    final sum + WTA + encode of the band's rows of the crop into out_dev, a full H x W
+ *                         uint16 map of which only the band's rows are written
+ * All three only enqueue on the slot's stream; sister_sync(slot) completes them. Outputs are bit-identical to
+ * sister_compute on one GPU (tests/test_bands.py).
+ */
+size_t sister_band_state_bytes(int w, int h, int disp_count);
+int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h, int channels,
+                       int disp_count, int mode, int band_row0, int band_row1);
+int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *state_in_dev, uint8_t *state_out_dev);
+int sister_band_finish(sister_ctx *ctx, int slot, uint16_t *out_dev);
+
 /* Plain device memory helpers so that a host language needs no CUDA binding of its own. */
 int sister_dev_alloc(sister_ctx *ctx, size_t bytes, void **dev_ptr);
 int sister_dev_free(sister_ctx *ctx, void *dev_ptr);

@@ -23,7 +23,8 @@ ABI_SYMBOLS = (
     "sister_create", "sister_destroy", "sister_compute", "sister_compute_batch", "sister_submit", "sister_wait",
     "sister_submit_device", "sister_sync", "sister_dev_alloc", "sister_dev_free", "sister_host_alloc", "sister_host_free", "sister_dev_upload",
     "sister_dev_download", "sister_set_profiling", "sister_region_begin", "sister_region_end", "sister_get_stage_ms", "sister_get_stage_launches",
-    "sister_get_launch_count", "sister_debug_fetch", "sister_set_test_taps", "sister_set_full_frame", "sister_test_sgm", "sister_strerror", "sister_last_error",
+    "sister_get_launch_count", "sister_debug_fetch", "sister_set_test_taps", "sister_set_full_frame",
+    "sister_band_state_bytes", "sister_band_submit", "sister_band_vertical", "sister_band_finish", "sister_test_sgm", "sister_strerror", "sister_last_error",
     "sister_version",
 )
 
@@ -104,6 +105,14 @@ def load_library():
     L.sister_set_test_taps.argtypes = [vp, C.c_int]
     L.sister_set_full_frame.restype = C.c_int
     L.sister_set_full_frame.argtypes = [vp, C.c_int]
+    L.sister_band_state_bytes.restype = C.c_size_t
+    L.sister_band_state_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.sister_band_submit.restype = C.c_int
+    L.sister_band_submit.argtypes = [vp, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.sister_band_vertical.restype = C.c_int
+    L.sister_band_vertical.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.sister_band_finish.restype = C.c_int
+    L.sister_band_finish.argtypes = [vp, C.c_int, vp]
     L.sister_test_sgm.restype = C.c_int
     L.sister_test_sgm.argtypes = [vp, _u8p, C.c_int, C.c_int, C.c_int, _u16p, _i16p]
     L.sister_strerror.restype = C.c_char_p
@@ -247,6 +256,22 @@ class Engine:
 
     def sync(self, slot: int = -1):
         self._chk(self.lib.sister_sync(self.ctx, slot))
+
+    # -- row bands: one frame over several GPUs (sister_b200/bands.py drives these)
+    def band_state_bytes(self, w: int, h: int, disp_count: int) -> int:
+        return int(self.lib.sister_band_state_bytes(w, h, disp_count))
+
+    def band_submit(self, slot: int, rig_ptr: int, w: int, h: int, channels: int, disp_count: int, mode: int, row0: int, row1: int):
+        vb = w * h * channels
+        varr = (C.c_void_p * 5)(*[C.c_void_p(rig_ptr + k * vb) for k in range(5)])
+        self._chk(self.lib.sister_band_submit(self.ctx, slot, varr, w, h, channels, disp_count, mode, row0, row1))
+
+    def band_vertical(self, slot: int, pass_: int, state_in_ptr: int, state_out_ptr: int):
+        self._chk(self.lib.sister_band_vertical(self.ctx, slot, pass_, C.c_void_p(state_in_ptr) if state_in_ptr else None,
+                                                C.c_void_p(state_out_ptr) if state_out_ptr else None))
+
+    def band_finish(self, slot: int, out_ptr: int):
+        self._chk(self.lib.sister_band_finish(self.ctx, slot, C.c_void_p(out_ptr)))
 
     # -- measurement / taps
     def set_profiling(self, on: bool):

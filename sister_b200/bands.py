@@ -1,0 +1,224 @@
+"""Row-band sharding of ONE large frame over the GPUs of one box (BASELINE.json configs[3]).
+
+Each rank owns a contiguous band of rows of the PADDED frame. The volumes (fused cost, eight path volumes, final sum)
+exist for the band only; staging, census, raw-cost WTA and masks are recomputed for the whole frame by every rank
+(include/sister_b200.h, "Row bands"). The row paths of SGM are band-local. The column and diagonal paths cross the
+bands: pass 0 flows from rank 0 down to rank G-1, pass 1 from rank G-1 up to rank 0, and each rank continues a path
+from the state its neighbour left (3 * Wp * D bytes per pass, exact -- no approximate overlapping halos). While rank t
+works on pass 0, rank G-1-t works on pass 1, so the two wavefronts overlap; everything else is fully parallel.
+
+`band_program` is the per-rank list of operations; the order of the two messages a pair of neighbours exchanges is the
+same on both sides (by the time slot the message is produced in), so blocking sends and receives cannot deadlock,
+neither over gloo (CPU tests) nor over NCCL (one ordered stream per peer).
+torch.distributed is the plumbing; the worker object is the Engine on the GPU box and a numpy stand-in in the tests.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+
+def band_rows(hp: int, world: int, rank: int) -> Tuple[int, int]:
+    """[row0, row1) of the padded frame rank `rank` owns: contiguous, the first hp % world ranks get one extra row."""
+    if world <= 0 or not (0 <= rank < world) or hp < world:
+        raise ValueError("bad band request")
+    base, extra = divmod(hp, world)
+    r0 = rank * base + min(rank, extra)
+    return r0, r0 + base + (1 if rank < extra else 0)
+
+
+def band_program(world: int, rank: int) -> List[Tuple[str, int, int]]:
+    """Operations of one rank, in order: ("recv", pass, peer) | ("compute", pass, -1) | ("send", pass, peer).
+
+    Pass 0 is computed by rank r in time slot r, pass 1 in slot world-1-r. The state of pass 0 goes r -> r+1 after slot r,
+    that of pass 1 r -> r-1 after slot world-1-r. A compute gets the key (its slot, 1, pass), a message -- on BOTH of its
+    ends -- the key (slot it is produced in, 2, pass); the program is the operations sorted by key. So a rank computes
+    before it communicates within a slot (the two wavefronts overlap), a state arrives before the compute that needs it,
+    and the messages between a pair of neighbours come in the same order on both ranks, which is what makes blocking
+    transfers safe."""
+    ops = []
+    for p in (0, 1):
+        slot = rank if p == 0 else world - 1 - rank
+        src = rank - 1 if p == 0 else rank + 1
+        dst = rank + 1 if p == 0 else rank - 1
+        if 0 <= src < world:
+            ops.append(((slot - 1, 2, p), ("recv", p, src)))       # produced by the neighbour in slot - 1: same key as its send
+        ops.append(((slot, 1, p), ("compute", p, -1)))
+        if 0 <= dst < world:
+            ops.append(((slot, 2, p), ("send", p, dst)))
+    ops.sort(key=lambda t: t[0])
+    prog = [o for _, o in ops]
+    # a receive must precede the compute that needs it (it does: slot - 1 < slot) -- checked, not assumed
+    for p in (0, 1):
+        names = [o[0] for o in prog if o[1] == p]
+        assert names == [n for n in ("recv", "compute", "send") if n in names]
+    return prog
+
+
+def simulate_programs(world: int) -> int:
+    """Run all ranks' programs with rendezvous (fully synchronous) transfers; returns the number of time steps, raises on
+    deadlock. Used by the CPU tests for every world size."""
+    progs = [band_program(world, r) for r in range(world)]
+    pc = [0] * world
+    have = [set() for _ in range(world)]  # passes whose input state has arrived
+    steps = 0
+    while any(pc[r] < len(progs[r]) for r in range(world)):
+        progress = False
+        matched = set()
+        for r in range(world):
+            if pc[r] >= len(progs[r]) or r in matched:
+                continue
+            kind, p, peer = progs[r][pc[r]]
+            if kind == "compute":
+                pc[r] += 1
+                progress = True
+            elif kind == "send":
+                if peer not in matched and pc[peer] < len(progs[peer]) and progs[peer][pc[peer]] == ("recv", p, r):
+                    pc[r] += 1
+                    pc[peer] += 1
+                    have[peer].add(p)
+                    matched.update((r, peer))
+                    progress = True
+        if not progress:
+            raise RuntimeError(f"deadlock at {[(progs[r][pc[r]] if pc[r] < len(progs[r]) else None) for r in range(world)]}")
+        steps += 1
+    return steps
+
+
+def compute_banded(worker, world: int, rank: int, group=None):
+    """Run this rank's band. `worker` provides
+         submit()                              -- whole-frame stages, fused cost and row paths of the band
+         vertical(pass, state_in, want_out)    -- column / diagonal paths of one pass; state_in / return value are torch
+                                                  uint8 tensors on the worker's device (or None)
+         new_state()                           -- an empty state tensor to receive into
+         finish()                              -- final WTA; returns this band's rows of the H x W map (torch int16 tensor
+                                                  holding the uint16 bits, possibly 0 rows)
+    Returns the band's rows."""
+    import torch.distributed as dist
+
+    worker.submit()
+    inbox = {}
+    outbox = {}
+    for kind, p, peer in band_program(world, rank):
+        if kind == "recv":
+            buf = worker.new_state()
+            dist.recv(buf, src=peer, group=group)
+            inbox[p] = buf
+        elif kind == "compute":
+            src = rank - 1 if p == 0 else rank + 1
+            dst = rank + 1 if p == 0 else rank - 1
+            outbox[p] = worker.vertical(p, inbox.get(p) if 0 <= src < world else None, 0 <= dst < world)
+        else:
+            dist.send(outbox[p], dst=peer, group=group)
+    return worker.finish()
+
+
+def run_bands_in_process(workers):
+    """All bands in ONE process (workers[r] is rank r's worker): the same programs, messages handed over directly.
+    This is how the tests run G bands on one GPU (one slot per band), and a way to bound the memory of a very large frame
+    on a single GPU. Returns the list of the bands' rows."""
+    world = len(workers)
+    for w in workers:
+        w.submit()
+    progs = [band_program(world, r) for r in range(world)]
+    pc = [0] * world
+    inbox = [dict() for _ in range(world)]
+    outbox = [dict() for _ in range(world)]
+    while any(pc[r] < len(progs[r]) for r in range(world)):
+        progress = False
+        for r in range(world):
+            if pc[r] >= len(progs[r]):
+                continue
+            kind, p, peer = progs[r][pc[r]]
+            if kind == "compute":
+                src = r - 1 if p == 0 else r + 1
+                dst = r + 1 if p == 0 else r - 1
+                outbox[r][p] = workers[r].vertical(p, inbox[r].get(p) if 0 <= src < world else None, 0 <= dst < world)
+            elif kind == "send":
+                if not (pc[peer] < len(progs[peer]) and progs[peer][pc[peer]] == ("recv", p, r)):
+                    continue
+                inbox[peer][p] = outbox[r][p]
+                pc[peer] += 1
+            else:
+                continue  # a receive completes together with the matching send
+            pc[r] += 1
+            progress = True
+        if not progress:
+            raise RuntimeError("band programs deadlocked")
+    return [w.finish() for w in workers]
+
+
+def crop_rows_of_band(D: int, H: int, row0: int, row1: int) -> Tuple[int, int]:
+    """Rows [a, b) of the H x W output map that the padded-frame band [row0, row1) holds (possibly empty)."""
+    a, b = max(row0, D) - D, min(row1, D + H) - D
+    return (a, b) if b > a else (0, 0)
+
+
+def gather_band_rows(local_rows, D: int, H: int, hp: int, dst: int = 0, group=None):
+    """Gather the ranks' rows (torch int16 [n_rows_local, W]) into the full [H, W] map on rank `dst` (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        return local_rows
+    spans = [crop_rows_of_band(D, H, *band_rows(hp, world, r)) for r in range(world)]
+    cap = max(b - a for a, b in spans)
+    w = local_rows.shape[1]
+    send = torch.zeros((cap, w), dtype=local_rows.dtype, device=local_rows.device)
+    send[: local_rows.shape[0]] = local_rows
+    send = send.contiguous().view(torch.uint8)  # the collective moves bytes
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([recv[r].view(local_rows.dtype)[: spans[r][1] - spans[r][0]] for r in range(world)], dim=0)
+
+
+class EngineBandWorker:
+    """The band worker on the GPU box: drives sister_band_* of one Engine (one context on this rank's GPU)."""
+
+    def __init__(self, engine, views, disp_count: int, rank: int, world: int, mode: int = 0, slot: int = 0):
+        import torch
+
+        self.torch = torch
+        self.eng = engine
+        v0 = views[0]
+        self.h, self.w = v0.shape[:2]
+        self.ch = 3 if v0.ndim == 3 else 1
+        self.D = disp_count
+        self.mode = mode
+        self.slot = slot
+        self.hp = self.h + 2 * disp_count
+        self.row0, self.row1 = band_rows(self.hp, world, rank)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.rig = engine.upload_rig(views)
+        self.state_bytes = engine.band_state_bytes(self.w, self.h, disp_count)
+        self.out = torch.zeros((self.h, self.w), dtype=torch.int16, device=self.device)
+
+    def new_state(self):
+        return self.torch.empty(self.state_bytes, dtype=self.torch.uint8, device=self.device)
+
+    def submit(self):
+        self.eng.band_submit(self.slot, self.rig, self.w, self.h, self.ch, self.D, self.mode, self.row0, self.row1)
+
+    def vertical(self, p: int, state_in, want_out: bool):
+        out = self.new_state() if want_out else None
+        if state_in is not None:
+            self.torch.cuda.current_stream().synchronize()  # the received state was written on torch's stream
+        self.eng.band_vertical(self.slot, p, state_in.data_ptr() if state_in is not None else 0, out.data_ptr() if want_out else 0)
+        if want_out:
+            self.eng.sync(self.slot)  # the library runs on its own stream: the state must be complete before it is sent
+        return out
+
+    def finish(self):
+        self.eng.band_finish(self.slot, self.out.data_ptr())
+        self.eng.sync(self.slot)
+        a, b = crop_rows_of_band(self.D, self.h, self.row0, self.row1)
+        return self.out[a:b]
+
+
+def as_uint16(t) -> np.ndarray:
+    return t.cpu().numpy().view(np.uint16)

@@ -34,6 +34,7 @@ struct Slot {
     unsigned mode_mask = 0;
     bool busy = false, host_io = false;
     bool full_frame = false; // the last run aggregated the whole padded frame (raw_disp is complete)
+    int band_r0 = 0, band_r1 = 0; // row band in progress (sister_band_*)
     // profiling
     std::vector<cudaEvent_t> ev_b, ev_e;
     std::vector<int> ev_stage;
@@ -383,6 +384,77 @@ int sister_submit_device(sister_ctx *ctx, int slot, const uint8_t *const views_d
     rc = run_pipeline(ctx, s, views_dev, w * channels, channels, d, mode_mask, out_dev);
     if (rc) return rc;
     s.host_io = false; // device submits are ordered by the slot's stream; nothing to hand back on the host
+    return SISTER_OK;
+}
+
+// ---- row bands: one frame split over several GPUs (include/sister_b200.h, "Row bands") ----
+
+size_t sister_band_state_bytes(int w, int h, int disp_count)
+{
+    (void)h;
+    return (size_t)3 * (size_t)(w + 2 * disp_count) * (size_t)disp_count;
+}
+
+int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h, int channels, int disp_count, int mode,
+                       int band_row0, int band_row1)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    if (!views_dev || (channels != 1 && channels != 3) || mode < 0 || mode > 2) { ctx->err = "bad views/channels/mode"; return SISTER_E_ARG; }
+    Dims d;
+    rc = check_shape(ctx, w, h, disp_count, d);
+    if (rc) return rc;
+    if (band_row0 < 0 || band_row1 > d.Hp || band_row0 >= band_row1) { ctx->err = "band rows must satisfy 0 <= row0 < row1 <= h + 2 * disp_count"; return SISTER_E_ARG; }
+    Slot &s = ctx->slots[slot];
+    SCK(cudaSetDevice(ctx->device));
+    if (s.busy && s.host_io) { ctx->err = "slot has an un-waited host submit"; return SISTER_E_BUSY; }
+    const ptrdiff_t stride = views_dev[1] - views_dev[0];
+    for (int k = 2; k < 5; k++)
+        if (views_dev[k] - views_dev[k - 1] != stride) { ctx->err = "device views must be equally spaced"; return SISTER_E_ARG; }
+    if (stride <= 0) { ctx->err = "device views must be in ascending address order"; return SISTER_E_ARG; }
+    const unsigned vm = mode == 0 ? 0xFu : mode == 1 ? 0x3u : 0xCu; // hpp:262-276
+    SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
+    // staging, census, raw-cost WTA and the masks need neighbours far outside the band (D rows for the vertical views,
+    // the whole map for the recursive median): every band computes them for the whole frame; the volumes -- fused cost,
+    // path bytes, i.e. all the memory and most of the time -- exist for the band's rows only
+    launch_prep(views_dev[0], (size_t)stride, w * channels, channels, d, s.d_oriented, s.st, ctx->lc);
+    launch_census(s.d_oriented, d, s.d_census, s.st, ctx->lc);
+    launch_match_wta(s.d_census, d, vm, s.d_wtaL, s.d_wtaR, s.st, ctx->lc);
+    launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, vm, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.st, ctx->lc);
+    launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused, s.d_status, s.st, ctx->lc, band_row0, band_row1);
+    launch_sgm_band(0, s.d_fused, d, band_row0, band_row1, nullptr, nullptr, s.d_paths, nullptr, nullptr, s.st, ctx->lc);
+    SCK(cudaGetLastError());
+    s.dims = d;
+    s.mode_mask = 1u << mode;
+    s.full_frame = false;
+    s.band_r0 = band_row0; s.band_r1 = band_row1;
+    s.host_io = false;
+    return SISTER_OK;
+}
+
+int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *state_in_dev, uint8_t *state_out_dev)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    Slot &s = ctx->slots[slot];
+    if (pass < 0 || pass > 1 || s.band_r1 <= s.band_r0) { ctx->err = "sister_band_submit first; pass is 0 or 1"; return SISTER_E_ARG; }
+    SCK(cudaSetDevice(ctx->device));
+    launch_sgm_band(1 + pass, s.d_fused, s.dims, s.band_r0, s.band_r1, state_in_dev, state_out_dev, s.d_paths, nullptr, nullptr, s.st, ctx->lc);
+    SCK(cudaGetLastError());
+    return SISTER_OK;
+}
+
+int sister_band_finish(sister_ctx *ctx, int slot, uint16_t *out_dev)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    Slot &s = ctx->slots[slot];
+    if (!out_dev || s.band_r1 <= s.band_r0) { ctx->err = "sister_band_submit first; out_dev must not be null"; return SISTER_E_ARG; }
+    SCK(cudaSetDevice(ctx->device));
+    launch_sgm_band(3, s.d_fused, s.dims, s.band_r0, s.band_r1, nullptr, nullptr, s.d_paths, nullptr, out_dev, s.st, ctx->lc);
+    SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
+    SCK(cudaGetLastError());
+    s.band_r0 = s.band_r1 = 0; // sister_sync(slot) completes the band and checks the status word
     return SISTER_OK;
 }
 

@@ -26,8 +26,9 @@ void launch_match_wta(const unsigned long long *census, const Dims &d, unsigned 
 void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims &d, unsigned view_mask, int16_t *medL,
                             int16_t *medR, int16_t *lr_final, uint8_t *masks, cudaStream_t st, LaunchCounter &lc);
 // fused volume C = sum_v mask_v * cost_v as uint8 (hpp:255-277); view_mask selects the mode's views
+// row_lo / row_hi: image rows to produce (whole tiles; the full frame is 0, Hp)
 void launch_fuse(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
-                 int *status, cudaStream_t st, LaunchCounter &lc);
+                 int *status, cudaStream_t st, LaunchCounter &lc, int row_lo = 0, int row_hi = -1);
 
 // ---- sgm.cu ----
 // 8-path SGM (sgm.cpp:26-455) on the uint8 fused volume: 8 one-byte path volumes (qvol, 8 * cells bytes), then
@@ -38,5 +39,12 @@ void launch_fuse(const unsigned long long *census, const uint8_t *masks, const D
 // are then written inside the crop only.
 void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, uint8_t *qvol, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
                 int *status, cudaStream_t st, LaunchCounter &lc);
+
+// One row band [band_r0, band_r1) of the padded frame (a large frame split over several GPUs),
+// crop-only aggregation. what: 0 = the band's row chains, 1 / 2 = the column and diagonal chains of pass 0 / pass 1
+// continued from state_in (the neighbouring band's state_out; null on the first band of the pass) and leaving their
+// state in state_out (null on the last), 3 = final sum / WTA / encode of the band's rows. State: 3 * Wp * D bytes.
+void launch_sgm_band(int what, const uint8_t *fused, const Dims &d, int band_r0, int band_r1, const uint8_t *state_in, uint8_t *state_out,
+                     uint8_t *qvol, int16_t *raw_disp, uint16_t *out, cudaStream_t st, LaunchCounter &lc);
 
 } // namespace sister

@@ -377,7 +377,7 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
 // grid (ceil(Wp/T), ceil(Hp/T)), block 32 * T, dynamic smem 4 * T * (T + D) u64 + 4 * T * T u64 + T * T bytes
 template <int T, int NK> // NK = D / 32 when D is a multiple of 32 (fully unrolled), 0 = any D
 __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__restrict__ census, const uint8_t *__restrict__ masks,
-                                                 Dims d, unsigned view_mask, uint8_t *__restrict__ fused, int *__restrict__ status)
+                                                 Dims d, unsigned view_mask, uint8_t *__restrict__ fused, int *__restrict__ status, int row_lo)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned s_any;
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
     const int D = d.D, P = T + D; // line pitch (T + D - 1 used)
     unsigned long long *sc1 = s + (size_t)4 * T * P;        // the tile's own (centre) codes, per view: [v][li][lj]
     uint8_t *smask = reinterpret_cast<uint8_t *>(sc1 + 4 * T * T);
-    const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
+    const int i0 = row_lo + blockIdx.y * T, j0 = blockIdx.x * T;
     const int tid = threadIdx.x, nthr = 32 * T;
     if (tid == 0) s_any = 0;
     __syncthreads();
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
 
 template <int T, int NK>
 static void launch_fuse_t(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
-                          int *status, cudaStream_t st)
+                          int *status, cudaStream_t st, int row_lo, int row_hi)
 {
     const size_t smem = (size_t)4 * T * (T + d.D) * 8 + (size_t)4 * T * T * 8 + T * T;
     static bool attr_done = false;
@@ -510,27 +510,29 @@ static void launch_fuse_t(const unsigned long long *census, const uint8_t *masks
         cudaFuncSetAttribute(k_fuse<T, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_done = true;
     }
-    dim3 grid((d.Wp + T - 1) / T, (d.Hp + T - 1) / T);
-    k_fuse<T, NK><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, status);
+    dim3 grid((d.Wp + T - 1) / T, (row_hi - row_lo + T - 1) / T);
+    k_fuse<T, NK><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, status, row_lo);
 }
 
 void launch_fuse(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
-                 int *status, cudaStream_t st, LaunchCounter &lc)
+                 int *status, cudaStream_t st, LaunchCounter &lc, int row_lo, int row_hi)
 {
+    if (row_hi < 0) row_hi = d.Hp;
+    if (row_hi <= row_lo) return;
     // 16 x 16 tiles while two blocks fit an SM (D <= 200), else 8 x 8
     if (d.D <= 200) {
         switch (d.D) {
-        case 64: launch_fuse_t<16, 2>(census, masks, d, view_mask, fused, status, st); break;
-        case 128: launch_fuse_t<16, 4>(census, masks, d, view_mask, fused, status, st); break;
-        case 192: launch_fuse_t<16, 6>(census, masks, d, view_mask, fused, status, st); break;
-        default: launch_fuse_t<16, 0>(census, masks, d, view_mask, fused, status, st); break;
+        case 64: launch_fuse_t<16, 2>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
+        case 128: launch_fuse_t<16, 4>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
+        case 192: launch_fuse_t<16, 6>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
+        default: launch_fuse_t<16, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
         }
     } else {
         switch (d.D) {
-        case 256: launch_fuse_t<8, 8>(census, masks, d, view_mask, fused, status, st); break;
-        case 384: launch_fuse_t<8, 12>(census, masks, d, view_mask, fused, status, st); break;
-        case 512: launch_fuse_t<8, 16>(census, masks, d, view_mask, fused, status, st); break;
-        default: launch_fuse_t<8, 0>(census, masks, d, view_mask, fused, status, st); break;
+        case 256: launch_fuse_t<8, 8>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
+        case 384: launch_fuse_t<8, 12>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
+        case 512: launch_fuse_t<8, 16>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
+        default: launch_fuse_t<8, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
         }
     }
     lc.add();

@@ -61,6 +61,18 @@ struct Roi {
 };
 __host__ __device__ inline bool roi_is_full(const Roi &r, const Dims &d) { return r.r0 == 0 && r.c0 == 0 && r.r1 == d.Hp && r.c1 == d.Wp; }
 
+// Row band [b0, b1) of the padded frame: what one GPU owns when a large frame is split over several (SURVEY section
+// 8(e)). Row chains of the band's rows are local. A column / diagonal chain is cut at the band's borders: it picks
+// up its state -- the clamped normalised vector a(d), one byte per disparity, D bytes per chain -- where the
+// neighbouring band left it (in[pass]) and leaves it for the next band (out[pass]). Pass 0 flows down (from the band
+// above, to the band below), pass 1 up. State layout: [path r1, r2, r3][first-line column of the chain][D].
+// The whole frame is the band b0 = 0, b1 = Hp with no state pointers.
+struct Band {
+    int b0, b1;
+    const uint8_t *in[2];
+    uint8_t *out[2];
+};
+
 // Chain numbering: nine sections, each padded to a multiple of `cpw` (chains per warp) so that a warp never mixes
 // sections; a padding slot repeats the section's last chain (it recomputes and rewrites the same bytes):
 //   0        kind 1   r0 on the first line of pass 0 / pass 1 (rows 0 and Hp-1; only when the region contains them)
@@ -73,20 +85,23 @@ struct Sections {
     int n[9], lo[9];   // chains in the section, first row / column
     long long o[10];   // first chain index (padded)
 };
-inline Sections chain_sections(const Dims &d, const Roi &r, int cpw)
+inline Sections chain_sections(const Dims &d, const Roi &r, const Band &bd, int cpw)
 {
     Sections s;
-    const bool first = r.r0 == 0, last = r.r1 == d.Hp;
+    const bool first = r.r0 == 0 && bd.b0 == 0, last = r.r1 == d.Hp && bd.b1 == d.Hp;
+    const int lo = r.r0 > bd.b0 ? r.r0 : bd.b0, hi = r.r1 < bd.b1 ? r.r1 : bd.b1; // rows of the region inside the band
     s.n[0] = (first ? 1 : 0) + (last ? 1 : 0);
     s.lo[0] = first ? 0 : 1; // pass of the section's first chain
-    s.lo[1] = r.r0 > 1 ? r.r0 : 1;                        // pass 0: row 0 is the first line
-    s.n[1] = r.r1 - s.lo[1];
-    s.lo[2] = r.r0;                                       // pass 1: row Hp-1 is the first line
-    s.n[2] = (r.r1 < d.Hp - 1 ? r.r1 : d.Hp - 1) - r.r0;
+    s.lo[1] = lo > 1 ? lo : 1;                            // pass 0: row 0 is the first line
+    s.n[1] = hi - s.lo[1];
+    s.lo[2] = lo;                                         // pass 1: row Hp-1 is the first line
+    s.n[2] = (hi < d.Hp - 1 ? hi : d.Hp - 1) - lo;
     for (int p = 0; p < 2; p++)
         for (int t = 0; t < 3; t++) {
+            // pass 0 walks rows [b0, min(b1, r1)), pass 1 rows [max(b0, r0), b1) downwards: none if that is empty
+            const bool live = p == 0 ? bd.b0 < (bd.b1 < r.r1 ? bd.b1 : r.r1) : (bd.b0 > r.r0 ? bd.b0 : r.r0) < bd.b1;
             s.lo[3 + 3 * p + t] = t == 1 ? r.c0 : 0;
-            s.n[3 + 3 * p + t] = t == 1 ? r.c1 - r.c0 : d.Wp;
+            s.n[3 + 3 * p + t] = !live ? 0 : t == 1 ? r.c1 - r.c0 : d.Wp;
         }
     s.o[0] = 0;
     for (int k = 0; k < 9; k++) {
@@ -97,12 +112,16 @@ inline Sections chain_sections(const Dims &d, const Roi &r, int cpw)
 }
 
 // returns the kind (0..2) or -1 when g is past the end
-__device__ __forceinline__ int chain_decode(const Dims &d, const Roi &r, const Sections &sec, long long g, Chain &ch, int &nsteps)
+__device__ __forceinline__ int chain_decode(const Dims &d, const Roi &r, const Band &bd, const Sections &sec, long long g, Chain &ch, int &nsteps,
+                                            int &section, long long &state_off, bool &imports, bool &exports)
 {
+    imports = exports = false;
+    state_off = 0;
     if (g >= sec.o[9]) return -1;
     int k = 0;
 #pragma unroll
     for (int q = 1; q < 9; q++) k += g >= sec.o[q];
+    section = k;
     const int idx = (int)min(g - sec.o[k], (long long)sec.n[k] - 1);
     if (k == 0) {
         const int p = sec.lo[0] + idx;
@@ -118,10 +137,26 @@ __device__ __forceinline__ int chain_decode(const Dims &d, const Roi &r, const S
     }
     const int p = (k - 3) / 3, type = (k - 3) % 3; // 0: r1, 1: r2, 2: r3
     const int dj = p ? -1 : 1, j1 = p ? d.Wp - 1 : 0, jl = p ? 0 : d.Wp - 1;
-    ch.i = p ? d.Hp - 1 : 0; ch.j = sec.lo[k] + idx; ch.si = dj;
+    const int c = sec.lo[k] + idx;                 // the chain's column on the first line of the pass
+    ch.si = dj;
     ch.sj = type == 0 ? dj : type == 1 ? 0 : -dj;
     ch.enter = type == 0 ? j1 : jl; // unused by r2 (sj = 0 never leaves the frame)
-    ch.vol = 4 * p + 1 + type; nsteps = p ? d.Hp - r.r0 : r.r1;
+    ch.vol = 4 * p + 1 + type;
+    // rows of this band the chain walks, and how many steps lie behind it when it enters the band
+    int done;
+    if (p == 0) {
+        const int end = bd.b1 < r.r1 ? bd.b1 : r.r1;
+        ch.i = bd.b0; nsteps = end - bd.b0; done = bd.b0;
+        imports = bd.b0 > 0; exports = end < r.r1;
+    } else {
+        const int end = bd.b0 > r.r0 ? bd.b0 : r.r0;
+        ch.i = bd.b1 - 1; nsteps = bd.b1 - end; done = d.Hp - bd.b1;
+        imports = bd.b1 < d.Hp; exports = end > r.r0;
+    }
+    int j = (c + (int)(((long long)ch.sj * done) % d.Wp)) % d.Wp; // a wrapped diagonal advances modulo Wp
+    if (j < 0) j += d.Wp;
+    ch.j = j;
+    state_off = ((long long)type * d.Wp + c) * d.D;
     return 2;
 }
 
@@ -160,7 +195,8 @@ template <bool DIAG> __device__ __forceinline__ bool in_roi(const Cursor &c, con
 // wrapped-diagonal loop, sj = 0 never wraps).
 template <int NR, int LPC, bool FULL, int KIND>
 __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane, uint8_t *__restrict__ q_lane, const LaneInfo<NR, LPC, FULL> &li,
-                                          const Walk &wk, Cursor first, int nsteps, int valid_bytes)
+                                          const Walk &wk, Cursor first, int nsteps, int valid_bytes,
+                                          const uint8_t *state_in = nullptr, uint8_t *state_out = nullptr)
 {
     constexpr bool DIAG = KIND == 2;
     uint32_t buf[kAhead][NR / 2];
@@ -184,6 +220,12 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
     // where L = C and nothing is added to the sum (sgm.cpp:103-138) -- exactly what a step from a = 0 produces
     // (q = 0, L = C). KIND 1 takes L = C in its first column and ignores the state.
     chain_set<NR, LPC, FULL>(cs, 0u, li);
+    if (KIND == 2 && state_in) { // warp-uniform: the chain continues from the band before (Band)
+        uint32_t w[NR / 2], a[NR];
+        load_cost<NR, FULL>(state_in, valid_bytes, w);
+        unpack_cost<NR>(w, a);
+        chain_resume<NR, LPC, FULL>(cs, a, li);
+    }
     // one step: consume buffer u (step s), refill it with step s + kAhead (past the end of the chain the last cell is
     // simply loaded again: an unconditional load keeps the buffer in place, a predicated one costs a copy per register)
     auto step = [&](const int u, const int s) {
@@ -216,21 +258,26 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
 #pragma unroll
     for (int u = 0; u < kAhead - 1; u++)
         if (s0 + u < nsteps) step(u, s0 + u); // warp-uniform
+    if (KIND == 2 && state_out) store_q<NR, FULL>(state_out, cs.a, valid_bytes); // a <= P2 fits a byte
 }
 
 // grid ceil(chains / (kChainWarps * 32 / LPC)), block kChainWarps * 32, no shared memory
 template <int NR, int LPC, bool FULL>
-__global__ void __launch_bounds__(kChainWarps * 32, ((NR <= 8 || (FULL && NR <= 12)) ? 24 : 16) / kChainWarps) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, Roi roi, Sections sec, uint8_t *__restrict__ qvol, unsigned kind_mask)
+__global__ void __launch_bounds__(kChainWarps * 32, ((NR <= 8 || (FULL && NR <= 12)) ? 24 : 16) / kChainWarps) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, Roi roi, Band band, Sections sec, uint8_t *__restrict__ qvol, unsigned section_mask,
+                                                                                                             long long first_block)
 {
     constexpr int CPW = 32 / LPC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     LaneInfo<NR, LPC, FULL> li;
     li.init(lane, d.D);
     Chain ch;
-    int nsteps = 0;
-    const int kind = chain_decode(d, roi, sec, ((long long)blockIdx.x * kChainWarps + warp) * CPW + lane / LPC, ch, nsteps);
+    int nsteps = 0, section = 0;
+    long long state_off = 0;
+    bool imports, exports;
+    const int kind = chain_decode(d, roi, band, sec, ((first_block + blockIdx.x) * kChainWarps + warp) * CPW + lane / LPC, ch, nsteps, section,
+                                  state_off, imports, exports);
     if (kind < 0) return; // warp-uniform: sections are padded to whole warps
-    if (!((kind_mask >> kind) & 1u)) return; // measurement aid (SISTER_DEBUG_PATH_KINDS), always 7 in the product
+    if (!((section_mask >> section) & 1u)) return; // band pipelines run the sections in separate launches
     const int D = d.D, Wp = d.Wp, D8 = D >> 3;
     const uint8_t *fused_lane = fused + li.sl * 2 * NR;
     uint8_t *q_lane = qvol + (size_t)ch.vol * (size_t)d.cells + li.sl * 2 * NR;
@@ -249,7 +296,12 @@ __global__ void __launch_bounds__(kChainWarps * 32, ((NR <= 8 || (FULL && NR <= 
     first.j = ch.j;
     if (kind == 1) run_chain<NR, LPC, FULL, 1>(fused_lane, q_lane, li, wk, first, nsteps, valid_bytes);
     else if (kind == 0) run_chain<NR, LPC, FULL, 0>(fused_lane, q_lane, li, wk, first, nsteps, valid_bytes);
-    else run_chain<NR, LPC, FULL, 2>(fused_lane, q_lane, li, wk, first, nsteps, valid_bytes);
+    else {
+        const int p = (section - 3) / 3;
+        const uint8_t *sin = (imports && band.in[p]) ? band.in[p] + state_off + li.sl * 2 * NR : nullptr;
+        uint8_t *sout = (exports && band.out[p]) ? band.out[p] + state_off + li.sl * 2 * NR : nullptr;
+        run_chain<NR, LPC, FULL, 2>(fused_lane, q_lane, li, wk, first, nsteps, valid_bytes, sin, sout);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- final sum + WTA + encode
@@ -324,25 +376,35 @@ __global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ f
 // ---------------------------------------------------------------------------------------------- launch
 
 // measurement aid: SISTER_DEBUG_PATH_KINDS=<bit mask of chain kinds to run> (results are then incomplete)
-static unsigned path_kind_mask()
+static unsigned debug_section_mask()
 {
     static int m = -1;
-    if (m < 0) { const char *e = getenv("SISTER_DEBUG_PATH_KINDS"); m = e ? atoi(e) & 7 : 7; }
+    if (m < 0) {
+        const char *e = getenv("SISTER_DEBUG_PATH_KINDS");
+        const int kinds = e ? atoi(e) & 7 : 7;
+        m = ((kinds & 2) ? 0x001 : 0) | ((kinds & 1) ? 0x006 : 0) | ((kinds & 4) ? 0x1F8 : 0);
+    }
     return (unsigned)m;
 }
 
 template <int NR, int LPC, bool FULL>
-static void launch_paths(const uint8_t *fused, const Dims &d, const Roi &roi, uint8_t *qvol, cudaStream_t st)
+static void launch_paths(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol, cudaStream_t st)
 {
     constexpr int CPW = 32 / LPC;
-    const Sections sec = chain_sections(d, roi, CPW);
-    const long long n = sec.o[9];
+    const Sections sec = chain_sections(d, roi, band, CPW);
+    // launch only the span of chain indices the requested sections cover
+    int k0 = 0, k1 = 9;
+    while (k0 < 9 && (!((section_mask >> k0) & 1u) || sec.n[k0] == 0)) k0++;
+    while (k1 > k0 && (!((section_mask >> (k1 - 1)) & 1u) || sec.n[k1 - 1] == 0)) k1--;
+    if (k0 >= k1) return;
     const long long per_block = (long long)kChainWarps * CPW;
-    k_sgm_paths<NR, LPC, FULL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, 0, st>>>(fused, d, roi, sec, qvol, path_kind_mask());
+    const long long first_block = sec.o[k0] / per_block, n = sec.o[k1] - first_block * per_block;
+    k_sgm_paths<NR, LPC, FULL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, 0, st>>>(fused, d, roi, band, sec, qvol, section_mask,
+                                                                                                       first_block);
 }
 
 template <int LPC, int NRMAX>
-static void launch_paths_lpc(const uint8_t *fused, const Dims &d, const Roi &roi, uint8_t *qvol, cudaStream_t st)
+static void launch_paths_lpc(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol, cudaStream_t st)
 {
     // disparities per lane = 2 * NR, NR even, chosen so that D fits in LPC lanes
     const int nr = 2 * ((d.D + 4 * LPC - 1) / (4 * LPC));
@@ -350,8 +412,8 @@ static void launch_paths_lpc(const uint8_t *fused, const Dims &d, const Roi &roi
 #define SISTER_PATHS_CASE(N)                                                                    \
     case N:                                                                                     \
         if constexpr (N <= NRMAX) {                                                             \
-            if (full) launch_paths<N, LPC, true>(fused, d, roi, qvol, st);                           \
-            else launch_paths<N, LPC, false>(fused, d, roi, qvol, st);                               \
+            if (full) launch_paths<N, LPC, true>(fused, d, roi, band, section_mask, qvol, st);                           \
+            else launch_paths<N, LPC, false>(fused, d, roi, band, section_mask, qvol, st);                               \
         }                                                                                       \
         break;
     switch (nr) {
@@ -361,24 +423,69 @@ static void launch_paths_lpc(const uint8_t *fused, const Dims &d, const Roi &roi
 #undef SISTER_PATHS_CASE
 }
 
+static Roi make_roi(const Dims &d, bool full_frame)
+{
+    Roi roi;
+    if (full_frame) { roi.r0 = 0; roi.r1 = d.Hp; roi.c0 = 0; roi.c1 = d.Wp; }
+    else { roi.r0 = d.D; roi.r1 = d.D + d.H; roi.c0 = d.D; roi.c1 = d.D + d.W; } // Rect(D, D, W, H), hpp:116-118
+    return roi;
+}
+
+static void launch_paths_any(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol,
+                             cudaStream_t st)
+{
+    // Whole-frame the kernel is bound by DRAM, crop-only by the ALU pipe with few chains left: measured on B200 at D = 192
+    // two chains per warp (twice the warps) beat four chains per warp by 4 % / 20 %.
+    static int lpc8_max = -1; // measurement aid: SISTER_DEBUG_LPC8_MAXD=<largest D that runs four chains per warp>
+    if (lpc8_max < 0) { const char *e = getenv("SISTER_DEBUG_LPC8_MAXD"); lpc8_max = e ? atoi(e) : 128; }
+    if (d.D <= lpc8_max && d.D <= 192) launch_paths_lpc<8, 12>(fused, d, roi, band, section_mask, qvol, st); // four chains per warp
+    else launch_paths_lpc<16, 16>(fused, d, roi, band, section_mask, qvol, st);                             // two (D <= 512, check_shape)
+}
+
+static void launch_final(const uint8_t *fused, const uint8_t *qvol, const Dims &d, const Roi &roi, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
+                         cudaStream_t st)
+{
+    const long long groups = ((long long)(roi.r1 - roi.r0) * (roi.c1 - roi.c0) + 3) / 4;
+    if (groups <= 0) return;
+    long long blocks = (groups + 7) / 8;
+    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    k_sgm_final<<<(unsigned)blocks, 256, 0, st>>>(fused, qvol, d, roi, sum, raw_disp, out);
+}
+
 void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, uint8_t *qvol, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
                 int *status, cudaStream_t st, LaunchCounter &lc)
 {
     (void)status;
-    Roi roi;
-    if (full_frame) { roi.r0 = 0; roi.r1 = d.Hp; roi.c0 = 0; roi.c1 = d.Wp; }
-    else { roi.r0 = d.D; roi.r1 = d.D + d.H; roi.c0 = d.D; roi.c1 = d.D + d.W; } // Rect(D, D, W, H), hpp:116-118
-    // The kernel is bound by DRAM (scattered 192-byte cells, reads and writes mixed), not by issue slots: measured on
-    // B200 at D = 192 two chains per warp (twice the warps) and four chains per warp run within 4 % of each other.
-    static int lpc8_max = -1; // measurement aid: SISTER_DEBUG_LPC8_MAXD=<largest D that runs four chains per warp>
-    if (lpc8_max < 0) { const char *e = getenv("SISTER_DEBUG_LPC8_MAXD"); lpc8_max = e ? atoi(e) : 128; }
-    if (d.D <= lpc8_max && d.D <= 192) launch_paths_lpc<8, 12>(fused, d, roi, qvol, st);         // four chains per warp
-    else launch_paths_lpc<16, 16>(fused, d, roi, qvol, st);                  // two chains per warp (D <= 512, check_shape)
+    const Roi roi = make_roi(d, full_frame);
+    Band band;
+    band.b0 = 0; band.b1 = d.Hp;
+    band.in[0] = band.in[1] = nullptr; band.out[0] = band.out[1] = nullptr;
+    launch_paths_any(fused, d, roi, band, debug_section_mask(), qvol, st);
     lc.add();
-    const long long groups = ((long long)(roi.r1 - roi.r0) * (roi.c1 - roi.c0) + 3) / 4;
-    long long blocks = (groups + 7) / 8;
-    if (blocks > 148LL * 64) blocks = 148LL * 64;
-    k_sgm_final<<<(unsigned)blocks, 256, 0, st>>>(fused, qvol, d, roi, sum, raw_disp, out);
+    launch_final(fused, qvol, d, roi, sum, raw_disp, out, st);
+    lc.add();
+}
+
+// ---- row bands (one band per GPU; crop-only aggregation). what: 0 = the band's row chains (r0 of both passes),
+// 1 = the column / diagonal chains of pass 0 (state_in from the band above, state_out for the band below),
+// 2 = those of pass 1 (state_in from the band below, state_out for the band above), 3 = final sum / WTA / encode of the
+// band's rows of the crop.
+void launch_sgm_band(int what, const uint8_t *fused, const Dims &d, int band_r0, int band_r1, const uint8_t *state_in, uint8_t *state_out,
+                     uint8_t *qvol, int16_t *raw_disp, uint16_t *out, cudaStream_t st, LaunchCounter &lc)
+{
+    Roi roi = make_roi(d, false);
+    Band band;
+    band.b0 = band_r0; band.b1 = band_r1;
+    band.in[0] = band.in[1] = nullptr; band.out[0] = band.out[1] = nullptr;
+    if (what == 3) {
+        roi.r0 = roi.r0 > band_r0 ? roi.r0 : band_r0;
+        roi.r1 = roi.r1 < band_r1 ? roi.r1 : band_r1;
+        launch_final(fused, qvol, d, roi, nullptr, raw_disp, out, st);
+    } else {
+        if (what == 1) { band.in[0] = state_in; band.out[0] = state_out; }
+        if (what == 2) { band.in[1] = state_in; band.out[1] = state_out; }
+        launch_paths_any(fused, d, roi, band, what == 0 ? 0x006u : what == 1 ? 0x038u : 0x1C0u, qvol, st);
+    }
     lc.add();
 }
 

@@ -150,6 +150,18 @@ __device__ __forceinline__ void chain_set(ChainState<NR> &st, uint32_t v2, const
     st.right = __byte_perm(st.b[0], (v2 + kP1x2) | li.dn_mask, 0x5432);
 }
 
+// continue a chain from a stored state vector a (a band border, sgm.cu Band)
+template <int NR, int LPC, bool FULL>
+__device__ __forceinline__ void chain_resume(ChainState<NR> &st, const uint32_t (&a)[NR], const LaneInfo<NR, LPC, FULL> &li)
+{
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+        st.a[k] = li.padded(a[k], k);
+        st.b[k] = st.a[k] + kP1x2;
+    }
+    end_neighbours<NR>(st.b, li.up_mask, li.dn_mask, st.left, st.right);
+}
+
 // The horizontal path on the first line of a pass (sgm.cpp:141-190): plain int arithmetic on the un-normalised
 // values, then saturate_cast<uint16>(uint8) truncation (types.h:28). The state carried along the line is the truncated
 // value Lq (b = Lq + P1) and its minimum (mm, both halves); the byte written to the path volume is the truncated

@@ -1,0 +1,44 @@
+"""Row bands on the GPU (sister_band_*, sister_b200/bands.py): G bands of one frame run on ONE GPU (one slot per band,
+states handed over in process) must reproduce sister_compute bit for bit -- every chain cut at every band border and
+continued from the stored state; and, when the box has 2+ GPUs, the same over NCCL with one process per GPU."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from sister_b200.synth import make_rig
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("w,h,D,world,mode", [(96, 64, 32, 2, 0), (100, 76, 40, 3, 1), (52, 88, 136, 5, 2), (64, 48, 16, 7, 0), (72, 60, 264, 2, 0),
+                                              (640, 480, 192, 4, 0)])
+def test_bands_on_one_gpu_equal_the_single_band_map(w, h, D, world, mode):
+    import sister_b200
+    from sister_b200.bands import EngineBandWorker, as_uint16, run_bands_in_process
+
+    views = make_rig(w, h, D, seed=31 + world, channels=3 if w < 600 else 1)
+    with sister_b200.Engine(w, h, D, n_slots=world) as eng:
+        want = eng.compute(views, D, mode_mask=1 << mode)[mode]
+        workers = [EngineBandWorker(eng, views, D, r, world, mode=mode, slot=r) for r in range(world)]
+        rows = run_bands_in_process(workers)
+        got = np.concatenate([as_uint16(r) for r in rows], axis=0)
+    assert got.shape == want.shape
+    assert (got == want).all(), f"{(got != want).sum()} pixels differ"
+
+
+def test_bands_over_nccl_when_the_box_has_two_gpus():
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU: the NCCL leg runs under gpurun --gpus 2 (scripts/run_bands.py)")
+    world = 2 if n < 4 else 4
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(ROOT, "scripts", "run_bands.py"), "--w", "320", "--h", "240", "--d", "64", "--check"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "bands == single GPU: True" in r.stdout
