@@ -2,7 +2,7 @@
 """One large frame over the GPUs of one box by row bands (BASELINE.json configs[3]); launch with torchrun, one rank per GPU:
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 \
-      scripts/run_bands.py --w 4096 --h 3072 --d 384 [--check] [--reps 3]
+      scripts/run_bands.py --width 4096 --height 3072 --disp 384 [--check] [--reps 3]
 
 Prints, on rank 0, the time of the banded frame (max over ranks, CUDA-synchronised wall clock around the whole banded call)
 and, with --check, whether the map equals the one a single GPU computes (rank 0 runs that as well; needs the memory of the
@@ -23,9 +23,9 @@ from sister_b200.bands import EngineBandWorker, as_uint16, compute_banded, gathe
 from sister_b200.synth import make_rig  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--w", type=int, default=4096)
-ap.add_argument("--h", type=int, default=3072)
-ap.add_argument("--d", type=int, default=384)
+ap.add_argument("--width", dest="w", type=int, default=4096)
+ap.add_argument("--height", dest="h", type=int, default=3072)
+ap.add_argument("--disp", dest="d", type=int, default=384)
 ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--check", action="store_true")

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sister_b200  # noqa: E402
 from sister_b200.synth import make_rig  # noqa: E402
 
-W, H, D = 1280, 960, 192
+W, H, D = (int(x) for x in os.environ.get("SISTER_SHAPE", "1280,960,192").split(","))
 views = make_rig(W, H, D, seed=1234, channels=3)
 with sister_b200.Engine(W, H, D, n_slots=1) as eng:
     rig = eng.upload_rig(views)

@@ -38,7 +38,7 @@ def test_bands_over_nccl_when_the_box_has_two_gpus():
         pytest.skip("one GPU: the NCCL leg runs under gpurun --gpus 2 (scripts/run_bands.py)")
     world = 2 if n < 4 else 4
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-                        "--master-port", "29517", os.path.join(ROOT, "scripts", "run_bands.py"), "--w", "320", "--h", "240", "--d", "64", "--check"],
+                        "--master-port", "29517", os.path.join(ROOT, "scripts", "run_bands.py"), "--width", "320", "--height", "240", "--disp", "64", "--check"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "bands == single GPU: True" in r.stdout
