@@ -111,6 +111,20 @@ int sister_sync(sister_ctx *ctx, int slot); /* slot < 0: all slots */
 int sister_set_full_frame(sister_ctx *ctx, int enabled);
 
 /*
+ * The two-view path of the reference (doStereo, hpp:122-150): AD-census cost of
+ * (center, side) (census.cpp:149-158), SGM on that raw volume (hpp:135), WTA left and right on the aggregated volume
+ * (hpp:137-138), in-place 3x3 median on both maps (hpp:139-140), LRC with threshold 5 (hpp:143).
+ *   center, side   grey uint8 images, h rows of w pixels, row_stride bytes apart; `side` is the view whose content
+ *                  appears shifted towards smaller columns (the "right" view of the rig, hpp:181)
+ *   out_left       h x w float: the disparity of `center`, -10 where the left-right check rejects it (doLRCheck)
+ *   out_right      h x w float or NULL: the median-filtered disparity of `side`
+ * No padding and no crop: the frame is the image, w % 4 == 0, h % 4 == 0, disp_count % 8 == 0. Runs on slot 0,
+ * synchronous. The frame must fit the context: w * h <= (max_w + 2 max_disp)(max_h + 2 max_disp).
+ */
+int sister_stereo(sister_ctx *ctx, const uint8_t *center, const uint8_t *side, int w, int h, size_t row_stride,
+                  int disp_count, float *out_left, float *out_right);
+
+/*
  * Row bands: ONE large frame split over several GPUs (BASELINE.json configs[3]).
  * Each GPU (one context per GPU, one process per GPU) owns the rows [band_row0, band_row1) of the PADDED frame
  * (0 .. h + 2 * disp_count). What is split is everything that is a volume: the fused cost (hpp:255-277), the

@@ -118,6 +118,15 @@ class Ref:
         self.lib.ref_sgm(_ptr(np.ascontiguousarray(img), _u8p), h, w, D, _ptr(np.ascontiguousarray(vol), _u16p), _ptr(out, _u16p))
         return out
 
+    def do_stereo(self, center, side, D):
+        """The reference's two-view path, composed from its own functions in the order of doStereo (hpp:122-150):
+        ad_census (hpp:132), sgm (hpp:135), WTA left / right on the aggregated volume (hpp:137-138), in-place median on
+        both maps (hpp:139-140), doLRCheck with threshold 5 (hpp:143). Returns (left, right) float32 maps."""
+        S = self.sgm(self.ad_census(center, side, D))
+        L, R = self.wta(S)
+        L, R = self.median_inplace(L), self.median_inplace(R)
+        return self.lrcheck(L, R, 5), R
+
     def multistereo_taps(self, views_padded, D, mode=0, want_volumes=True):
         hp, wp = views_padded[0].shape
         arr, keep = _views_array(views_padded)
@@ -226,6 +235,15 @@ class Oracle:
         if rc != 0:
             raise MemoryError("so_sgm")
         return out
+
+    def do_stereo(self, center, side, D):
+        """The reference's two-view path, composed from its own functions in the order of doStereo (hpp:122-150):
+        ad_census (hpp:132), sgm (hpp:135), WTA left / right on the aggregated volume (hpp:137-138), in-place median on
+        both maps (hpp:139-140), doLRCheck with threshold 5 (hpp:143). Returns (left, right) float32 maps."""
+        S = self.sgm(self.ad_census(center, side, D))
+        L, R = self.wta(S)
+        L, R = self.median_inplace(L), self.median_inplace(R)
+        return self.lrcheck(L, R, 5), R
 
     def multistereo(self, views_padded, D, mode=0, want_volumes=True):
         hp, wp = views_padded[0].shape

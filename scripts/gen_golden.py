@@ -90,5 +90,38 @@ def main():
     print("stage_kats ok", os.path.getsize(os.path.join(OUT, "stage_kats.npz")), "bytes")
 
 
+# (W, H, D, seed): two-view pairs (center, right) for doStereo (hpp:122-150), frame = image, W % 4 == H % 4 == 0
+STEREO = [(96, 64, 32, 2001), (72, 60, 24, 2002), (128, 96, 64, 2003), (64, 80, 8, 2004)]
+
+
+def stereo():
+    """tests/golden/stereo_pairs.npz: the reference's two-view path composed from its own functions in doStereo's order
+    (oracle.Ref.do_stereo), plus SGM known answers on uint8 volumes that contain the 255 marker (the first-line
+    255 -> 0 substitution of sgm.cpp:109,123,146, which the fused volumes of the 5-view path never exercise)."""
+    oracle.build(ref=True)
+    ref = oracle.Ref()
+    rec = {}
+    for k, (w, h, D, seed) in enumerate(STEREO):
+        views = make_rig(w, h, D, seed=seed, kind="smooth", channels=1)
+        L, R = ref.do_stereo(views[0], views[1], D)
+        rec[f"shape_{k}"] = np.array([w, h, D, seed])
+        rec[f"left_{k}"] = L.astype(np.int16)
+        rec[f"right_{k}"] = R.astype(np.int16)
+    rng = np.random.default_rng(20261018)
+    for k, (h, w, D) in enumerate([(20, 24, 16), (14, 36, 40), (24, 20, 192)]):
+        vol = rng.integers(0, 253, (h, w, D), dtype=np.uint16)
+        vol[rng.random((h, w, D)) < 0.15] = 255
+        vol[0][rng.random((w, D)) < 0.4] = 255
+        vol[-1][rng.random((w, D)) < 0.4] = 255
+        rec[f"sgm255_in_{k}"] = vol.astype(np.uint8)
+        rec[f"sgm255_out_{k}"] = ref.sgm(vol)
+    np.savez_compressed(os.path.join(OUT, "stereo_pairs.npz"), **rec)
+    print("stereo_pairs ok", os.path.getsize(os.path.join(OUT, "stereo_pairs.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--stereo-only" in sys.argv:
+        stereo()
+    else:
+        main()
+        stereo()

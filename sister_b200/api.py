@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "sister_submit_device", "sister_sync", "sister_dev_alloc", "sister_dev_free", "sister_host_alloc", "sister_host_free", "sister_dev_upload",
     "sister_dev_download", "sister_set_profiling", "sister_region_begin", "sister_region_end", "sister_get_stage_ms", "sister_get_stage_launches",
     "sister_get_launch_count", "sister_debug_fetch", "sister_set_test_taps", "sister_set_full_frame",
-    "sister_band_state_bytes", "sister_band_submit", "sister_band_vertical", "sister_band_finish", "sister_test_sgm", "sister_strerror", "sister_last_error",
+    "sister_stereo", "sister_band_state_bytes", "sister_band_submit", "sister_band_vertical", "sister_band_finish", "sister_test_sgm", "sister_strerror", "sister_last_error",
     "sister_version",
 )
 
@@ -105,6 +105,8 @@ def load_library():
     L.sister_set_test_taps.argtypes = [vp, C.c_int]
     L.sister_set_full_frame.restype = C.c_int
     L.sister_set_full_frame.argtypes = [vp, C.c_int]
+    L.sister_stereo.restype = C.c_int
+    L.sister_stereo.argtypes = [vp, _u8p, _u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.sister_band_state_bytes.restype = C.c_size_t
     L.sister_band_state_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     L.sister_band_submit.restype = C.c_int
@@ -256,6 +258,19 @@ class Engine:
 
     def sync(self, slot: int = -1):
         self._chk(self.lib.sister_sync(self.ctx, slot))
+
+    def stereo(self, center, side, disp_count: int):
+        """The reference's two-view path (doStereo, hpp:122-150) on grey uint8 images: returns (left, right) float32 maps,
+        left = LR-checked disparity of `center` (-10 = rejected), right = median-filtered disparity of `side`."""
+        c = np.ascontiguousarray(center, dtype=np.uint8)
+        r = np.ascontiguousarray(side, dtype=np.uint8)
+        h, w = c.shape
+        outL = np.zeros((h, w), np.float32)
+        outR = np.zeros((h, w), np.float32)
+        fp = C.POINTER(C.c_float)
+        self._chk(self.lib.sister_stereo(self.ctx, c.ctypes.data_as(_u8p), r.ctypes.data_as(_u8p), w, h, w, disp_count,
+                                         outL.ctypes.data_as(fp), outR.ctypes.data_as(fp)))
+        return outL, outR
 
     # -- row bands: one frame over several GPUs (sister_b200/bands.py drives these)
     def band_state_bytes(self, w: int, h: int, disp_count: int) -> int:

@@ -632,6 +632,73 @@ int sister_debug_fetch(sister_ctx *ctx, int slot, int what, void *host_dst, size
     return SISTER_OK;
 }
 
+// The two-view path of the reference (doStereo, hpp:122-150): AD-census cost of (center, side), SGM on that raw volume,
+// WTA left and right on the aggregated volume, in-place median on both maps, LRC. No padding, no crop: the frame is the
+// image. Every kernel is one of the 5-view path's, run for view 0 ("right", rotation 0) only.
+int sister_stereo(sister_ctx *ctx, const uint8_t *center, const uint8_t *side, int w, int h, size_t row_stride, int disp_count,
+                  float *out_left, float *out_right)
+{
+    if (!ctx || !center || !side || !out_left) return SISTER_E_ARG;
+    if (w <= 0 || h <= 0 || disp_count <= 0 || row_stride < (size_t)w) { ctx->err = "bad stereo arguments"; return SISTER_E_ARG; }
+    if (disp_count % 8 != 0) { ctx->err = "disp_count must be a multiple of 8 (sgm.cpp:268)"; return SISTER_E_SHAPE; }
+    if (disp_count > 512) { ctx->err = "disp_count above 512 is not supported"; return SISTER_E_SHAPE; }
+    if (w % 4 != 0 || h % 4 != 0) { ctx->err = "w and h must be multiples of 4 (postprocess.cpp:18)"; return SISTER_E_SHAPE; }
+    if (w < 16 || h < 16) { ctx->err = "frame too small for the 9x7 census"; return SISTER_E_SHAPE; }
+    Dims d;
+    d.W = 0; d.H = 0; d.D = disp_count; d.Wp = w; d.Hp = h;
+    d.px = (long long)w * h;
+    d.cells = d.px * disp_count;
+    if (d.cells / 8 > 0x7F000000LL) { ctx->err = "cost volume above 1.7e10 cells (32-bit cursor offsets in sgm.cu)"; return SISTER_E_SHAPE; }
+    if (d.px > ctx->px_max || d.cells > ctx->cells_max || (size_t)2 * d.px > ctx->in_bytes_max) {
+        ctx->err = "stereo pair larger than the capacity given to sister_create";
+        return SISTER_E_CAPACITY;
+    }
+    Slot &s = ctx->slots[0];
+    if (s.busy) { ctx->err = "slot busy"; return SISTER_E_BUSY; }
+    SCK(cudaSetDevice(ctx->device));
+    const size_t px = (size_t)d.px;
+    for (int k = 0; k < 2; k++) {
+        const uint8_t *src = k ? side : center;
+        uint8_t *dst = s.h_in + k * px;
+        if (row_stride == (size_t)w) memcpy(dst, src, px);
+        else for (int i = 0; i < h; i++) memcpy(dst + (size_t)i * w, src + (size_t)i * row_stride, (size_t)w);
+    }
+    // oriented images 0 / 1 = the pair as it is (view 0 is the identity orientation, hpp:56-58)
+    SCK(cudaMemcpyAsync(s.d_oriented, s.h_in, 2 * px, cudaMemcpyHostToDevice, s.st));
+    SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
+    if (!s.d_sum) SCK(cudaMalloc((void **)&s.d_sum, (size_t)ctx->cells_max * 2));
+    ctx->lc.cur_stage = SISTER_STAGE_CENSUS;
+    launch_census(s.d_oriented, d, s.d_census, s.st, ctx->lc);
+    // the raw volume of ad_census (census.cpp:54-146, 255 markers and all) is the "fused" volume of view 0 under an
+    // all-ones mask: k_fuse evaluates the literal per-cell formula wherever the fast path does not apply
+    ctx->lc.cur_stage = SISTER_STAGE_FUSE;
+    SCK(cudaMemsetAsync(s.d_masks, 1, px, s.st));
+    launch_fuse(s.d_census, s.d_masks, d, 0x1u, s.d_fused, s.d_status, s.st, ctx->lc);
+    // SGM (hpp:135) + WTA-left (hpp:137) in the final sweep; the aggregated volume is kept for WTA-right (hpp:138)
+    ctx->lc.cur_stage = SISTER_STAGE_AGGREGATE;
+    launch_sgm(s.d_fused, d, true, s.d_paths, s.d_sum, s.d_wtaL, nullptr, s.d_status, s.st, ctx->lc);
+    launch_wta_right_sum(s.d_sum, d, s.d_wtaR, s.st, ctx->lc);
+    // median on both maps (hpp:139-140), LRC (hpp:143)
+    ctx->lc.cur_stage = SISTER_STAGE_MASK;
+    launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, 0x1u, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.st, ctx->lc);
+    SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
+    SCK(cudaGetLastError());
+    SCK(cudaStreamSynchronize(s.st));
+    SCK(cudaMemsetAsync(s.d_masks, 0, px, s.st)); // the 5-view path expects untouched masks to be 0
+    if (!ctx->taps) { SCK(cudaFree(s.d_sum)); s.d_sum = nullptr; }
+    s.dims = d;
+    s.full_frame = true;
+    if (*s.h_status & ~kStatusFusedOverflow) { ctx->err = "kernel invariant violated"; return SISTER_E_INTERNAL; }
+    std::vector<int16_t> tmp(px);
+    SCK(cudaMemcpy(tmp.data(), s.d_lr, px * 2, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < px; k++) out_left[k] = (float)tmp[k];
+    if (out_right) {
+        SCK(cudaMemcpy(tmp.data(), s.d_medR, px * 2, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < px; k++) out_right[k] = (float)tmp[k];
+    }
+    return SISTER_OK;
+}
+
 int sister_test_sgm(sister_ctx *ctx, const uint8_t *fused, int w, int h, int disp_count, uint16_t *sum, int16_t *disp)
 {
     if (!ctx || !fused || !sum) return SISTER_E_ARG;

@@ -40,6 +40,9 @@ void launch_fuse(const unsigned long long *census, const uint8_t *masks, const D
 void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, uint8_t *qvol, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
                 int *status, cudaStream_t st, LaunchCounter &lc);
 
+// WTARight_SSE on the aggregated volume (hpp:138): int16 map Hp x Wp
+void launch_wta_right_sum(const uint16_t *sum, const Dims &d, int16_t *outR, cudaStream_t st, LaunchCounter &lc);
+
 // One row band [band_r0, band_r1) of the padded frame (a large frame split over several GPUs),
 // crop-only aggregation. what: 0 = the band's row chains, 1 / 2 = the column and diagonal chains of pass 0 / pass 1
 // continued from state_in (the neighbouring band's state_out; null on the first band of the pass) and leaving their

@@ -16,7 +16,8 @@
 //         r0 at the start of a row: L = 0, m = 0               -> a = 0 everywhere   => Q = 0    (sgm.cpp:215-216)
 //         first line of a pass: L1 = L2 = L3 = C, m = min C    -> a = min(C - min C, P2), nothing added to the sum
 //         first line, r0: int32 arithmetic + 8-bit truncation  -> first_line_step (sgm.cpp:141-190, types.h:28)
-//     The "cost == 255 -> 0" substitution of sgm.cpp:109,123,146 can never fire on C <= 252.
+//     The "cost == 255 -> 0" substitution of sgm.cpp:109,123,146 can never fire on a fused C <= 252; it is applied all
+//     the same (first lines only), because the two-view path (sister_stereo, hpp:122-150) aggregates a raw volume.
 //   * A chain does not touch the sum volume. It emits the penalty term Q(d) = L'(d) - C(d) in [0, P2] as ONE BYTE per
 //     cell into the path's own volume (a diagonal chain that leaves the frame re-enters at the opposite border with
 //     a = P2, so every column/diagonal chain has exactly Hp steps and every cell of a path volume is written once).
@@ -196,7 +197,7 @@ template <bool DIAG> __device__ __forceinline__ bool in_roi(const Cursor &c, con
 template <int NR, int LPC, bool FULL, int KIND>
 __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane, uint8_t *__restrict__ q_lane, const LaneInfo<NR, LPC, FULL> &li,
                                           const Walk &wk, Cursor first, int nsteps, int valid_bytes,
-                                          const uint8_t *state_in = nullptr, uint8_t *state_out = nullptr)
+                                          const uint8_t *state_in = nullptr, uint8_t *state_out = nullptr, bool starts_on_first_line = true)
 {
     constexpr bool DIAG = KIND == 2;
     uint32_t buf[kAhead][NR / 2];
@@ -207,6 +208,12 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
     for (int t = 0; t < kAhead; t++) {
         load_cost<NR, FULL>(fused_lane + (long long)ld.off8 * 8, valid_bytes, buf[t]); // nsteps >= 12 (check_shape, sister_test_sgm)
         advance<DIAG>(ld, wk); // nsteps > kAhead: ld now points at step kAhead
+    }
+    // the first line of a pass reads an invalid cost (255, census.cpp:76) as 0 (sgm.cpp:109,123,146); fused volumes
+    // never hold 255 (match.cu), the raw two-view volume of sister_stereo does
+    if (KIND == 2 && starts_on_first_line) {
+#pragma unroll
+        for (int k = 0; k < NR / 2; k++) buf[0][k] &= ~__vcmpeq4(buf[0][k], 0xFFFFFFFFu);
     }
     pf = ld;
 #pragma unroll 1
@@ -230,6 +237,10 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
     // simply loaded again: an unconditional load keeps the buffer in place, a predicated one costs a copy per register)
     auto step = [&](const int u, const int s) {
         uint32_t c[NR], q[NR];
+        if constexpr (KIND == 1) { // every cell of this chain lies on the first line
+#pragma unroll
+            for (int k = 0; k < NR / 2; k++) buf[u][k] &= ~__vcmpeq4(buf[u][k], 0xFFFFFFFFu);
+        }
         unpack_cost<NR>(buf[u], c);
         load_cost<NR, FULL>(fused_lane + (long long)ld.off8 * 8, valid_bytes, buf[u]);
         if (s + kAhead + 1 < nsteps) advance<DIAG>(ld, wk);
@@ -300,7 +311,7 @@ __global__ void __launch_bounds__(kChainWarps * 32, ((NR <= 8 || (FULL && NR <= 
         const int p = (section - 3) / 3;
         const uint8_t *sin = (imports && band.in[p]) ? band.in[p] + state_off + li.sl * 2 * NR : nullptr;
         uint8_t *sout = (exports && band.out[p]) ? band.out[p] + state_off + li.sl * 2 * NR : nullptr;
-        run_chain<NR, LPC, FULL, 2>(fused_lane, q_lane, li, wk, first, nsteps, valid_bytes, sin, sout);
+        run_chain<NR, LPC, FULL, 2>(fused_lane, q_lane, li, wk, first, nsteps, valid_bytes, sin, sout, !imports);
     }
 }
 
@@ -371,6 +382,33 @@ __global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ f
             if (out && oi >= 0 && oi < d.H && oj >= 0 && oj < d.W) out[(size_t)oi * d.W + oj] = (uint16_t)min(disp * 255, 65535);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------- WTA-right on S (two-view path)
+
+// WTARight_SSE on the aggregated volume (hpp:138, postprocess.cpp:187-315, uniqueness 1): R(i, j) = first-index argmin
+// over d <= min(w-1-j, D-1) of S[i][j+d][d]. One warp per pixel, lanes over d; a row of S stays in L2 while its
+// pixels are visited.
+__global__ void __launch_bounds__(256) k_wta_right_sum(const uint16_t *__restrict__ sum, Dims d, int16_t *__restrict__ outR)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long pix = warp0; pix < d.px; pix += nwarps) {
+        const int j = (int)(pix % d.Wp);
+        const int dmax = min(d.Wp - 1 - j, d.D - 1);
+        unsigned best = 0xFFFFFFFFu;
+        for (int dd = lane; dd <= dmax; dd += 32) best = min(best, ((unsigned)sum[(size_t)(pix + dd) * d.D + dd] << 16) | (unsigned)dd);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(kFull, best, o));
+        if (lane == 0) outR[pix] = (int16_t)(best & 0xFFFFu);
+    }
+}
+
+void launch_wta_right_sum(const uint16_t *sum, const Dims &d, int16_t *outR, cudaStream_t st, LaunchCounter &lc)
+{
+    k_wta_right_sum<<<148 * 8, 256, 0, st>>>(sum, d, outR);
+    lc.add();
 }
 
 // ---------------------------------------------------------------------------------------------- launch
