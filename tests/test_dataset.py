@@ -13,6 +13,7 @@ from sister_b200.dataset import (SisterDataset, VIEW_ORDER, decode_disparity, de
 from sister_b200.synth import make_rig  # noqa: E402
 
 W, H, D, FOCAL = 96, 64, 32, 800.0
+PLANE = int(round(D / 3.0))  # synth.disparity_field(kind="plane") rounds D / 3
 
 
 def write_rig(folder, views):
@@ -22,14 +23,14 @@ def write_rig(folder, views):
 
 
 def build_tree(root):
-    """two objects, one distance each, two baselines; the plane rigs have disparity D // 3 everywhere"""
+    """two objects, one distance each, two baselines; the plane rigs have disparity PLANE = round(D / 3) everywhere"""
     rigs = {}
     for k, obj in enumerate(("washer", "hexa_screw")):
         for b, base in enumerate(("025mm", "050mm")):
             views = make_rig(W, H, D, seed=50 + 2 * k + b, kind="plane", noise=0, channels=3)
             write_rig(os.path.join(root, obj, "10cm", base), views)
             rigs[(obj, base)] = views
-        depth = np.full((H, W), FOCAL * 0.025 / (D // 3), np.float32)
+        depth = np.full((H, W), FOCAL * 0.025 / PLANE, np.float32)
         depth[:4] = 0  # invalid ground truth rows
         assert cv2.imwrite(os.path.join(root, obj, "10cm", "gt_depth.exr"), depth)
     return rigs
@@ -68,7 +69,7 @@ def test_run_dataset_with_a_stand_in_compute(tmp_path):
 
     def compute(batch, disp_count):
         assert disp_count == D and all(len(r) == 5 for r in batch)
-        m = np.full((H, W), (D // 3) * 255, np.uint16)
+        m = np.full((H, W), PLANE * 255, np.uint16)
         return [[m, m, None] for _ in batch]
 
     rep = run_dataset(ds, compute, D, FOCAL, batch=3)
