@@ -83,6 +83,7 @@ int check_shape(sister_ctx *ctx, int w, int h, int D, Dims &d)
     d.W = w; d.H = h; d.D = D; d.Wp = w + 2 * D; d.Hp = h + 2 * D;
     d.px = (long long)d.Wp * d.Hp;
     d.cells = d.px * D;
+    set_cell_order(d);
     if (d.cells / 8 > 0x7F000000LL) { ctx->err = "cost volume above 1.7e10 cells (32-bit cursor offsets in sgm.cu)"; return SISTER_E_SHAPE; }
     if (w > ctx->max_w || h > ctx->max_h || D > ctx->max_d || d.px > ctx->px_max || d.cells > ctx->cells_max) {
         ctx->err = "rig larger than the capacity given to sister_create";
@@ -600,6 +601,21 @@ int sister_get_stage_launches(sister_ctx *ctx, int slot, int *count, int n)
 
 uint64_t sister_get_launch_count(sister_ctx *ctx) { return ctx ? ctx->lc.total : 0; }
 
+// the fused volume is stored in the path kernel's cell order (Dims, common.cuh); taps and test volumes are in natural order
+static void reorder_cells(const Dims &d, uint8_t *buf, size_t ncells, bool to_natural)
+{
+    if (!d.interleaved) return;
+    std::vector<int> disp_of(d.D);
+    for (int p = 0; p < d.D; p++) disp_of[p] = cell_disp(d, p);
+    std::vector<uint8_t> tmp(d.D);
+    for (size_t c = 0; c < ncells; c++) {
+        uint8_t *cell = buf + c * d.D;
+        if (to_natural) { for (int p = 0; p < d.D; p++) tmp[disp_of[p]] = cell[p]; }
+        else { for (int p = 0; p < d.D; p++) tmp[p] = cell[disp_of[p]]; }
+        memcpy(cell, tmp.data(), d.D);
+    }
+}
+
 int sister_debug_fetch(sister_ctx *ctx, int slot, int what, void *host_dst, size_t bytes)
 {
     int rc = slot_ok(ctx, slot);
@@ -629,6 +645,7 @@ int sister_debug_fetch(sister_ctx *ctx, int slot, int what, void *host_dst, size
     }
     if (bytes > have) { ctx->err = "tap smaller than requested"; return SISTER_E_ARG; }
     SCK(cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost));
+    if (what == SISTER_TAP_FUSED) reorder_cells(s.dims, static_cast<uint8_t *>(host_dst), bytes / (size_t)s.dims.D, true);
     return SISTER_OK;
 }
 
@@ -648,6 +665,7 @@ int sister_stereo(sister_ctx *ctx, const uint8_t *center, const uint8_t *side, i
     d.W = 0; d.H = 0; d.D = disp_count; d.Wp = w; d.Hp = h;
     d.px = (long long)w * h;
     d.cells = d.px * disp_count;
+    set_cell_order(d);
     if (d.cells / 8 > 0x7F000000LL) { ctx->err = "cost volume above 1.7e10 cells (32-bit cursor offsets in sgm.cu)"; return SISTER_E_SHAPE; }
     if (d.px > ctx->px_max || d.cells > ctx->cells_max || (size_t)2 * d.px > ctx->in_bytes_max) {
         ctx->err = "stereo pair larger than the capacity given to sister_create";
@@ -707,11 +725,18 @@ int sister_test_sgm(sister_ctx *ctx, const uint8_t *fused, int w, int h, int dis
     d.W = 0; d.H = 0; d.D = disp_count; d.Wp = w; d.Hp = h;
     d.px = (long long)w * h;
     d.cells = d.px * disp_count;
+    set_cell_order(d);
     if (d.px > ctx->px_max || d.cells > ctx->cells_max) { ctx->err = "sgm test volume exceeds capacity"; return SISTER_E_CAPACITY; }
     Slot &s = ctx->slots[0];
     if (s.busy) return SISTER_E_BUSY;
     SCK(cudaSetDevice(ctx->device));
-    SCK(cudaMemcpyAsync(s.d_fused, fused, (size_t)d.cells, cudaMemcpyHostToDevice, s.st));
+    if (d.interleaved) {
+        std::vector<uint8_t> ordered(fused, fused + (size_t)d.cells);
+        reorder_cells(d, ordered.data(), (size_t)d.px, false);
+        SCK(cudaMemcpy(s.d_fused, ordered.data(), (size_t)d.cells, cudaMemcpyHostToDevice));
+    } else {
+        SCK(cudaMemcpyAsync(s.d_fused, fused, (size_t)d.cells, cudaMemcpyHostToDevice, s.st));
+    }
     SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
     if (!s.d_sum) SCK(cudaMalloc((void **)&s.d_sum, (size_t)ctx->cells_max * 2));
     ctx->lc.cur_stage = SISTER_STAGE_AGGREGATE;

@@ -28,7 +28,33 @@ struct Dims {
     int Wp, Hp;    // padded
     long long px;  // Wp * Hp
     long long cells; // px * D
+    // Byte order inside a cell (the D bytes of one pixel) of the fused-cost volume and of the 8 path volumes, fixed by how
+    // the path kernel (sgm.cu) spreads a chain over lanes: `lpc` lanes per chain, 2 * nr disparities per lane. When the
+    // lanes are exactly full (D == 2 * lpc * nr: 32, 64, 96, 128, 192, 256, ... 512) the cell is stored LANE-INTERLEAVED:
+    //     32-bit word (t, sl), t < nr / 2, sl < lpc, at byte 4 * (t * lpc + sl), holds the disparities
+    //     sl * 2nr + { 2t, 2t + 1, nr + 2t, nr + 2t + 1 }
+    // which is the pair of packed 16-bit registers (2t, 2t + 1) of lane sl with the odd one shifted up by a byte: a load
+    // or store instruction of a chain covers 4 * lpc contiguous bytes, and bytes <-> registers is two instructions per
+    // word. Otherwise (interleaved == 0) the cell is in natural disparity order. Producers (k_fuse), consumers
+    // (k_sgm_paths, k_sgm_final) and the test taps (api.cu) all go through cell_disp / cell_pos.
+    int lpc, nr, lpc_shift, interleaved;
 };
+
+// disparity stored at byte `pos` of a cell, and its inverse
+__host__ __device__ inline int cell_disp(const Dims &d, int pos)
+{
+    if (!d.interleaved) return pos;
+    const int word = pos >> 2, b = pos & 3, t = word >> d.lpc_shift, sl = word & (d.lpc - 1);
+    return sl * 2 * d.nr + 2 * t + (b & 1) + (b >> 1) * d.nr;
+}
+__host__ __device__ inline int cell_pos(const Dims &d, int disp)
+{
+    if (!d.interleaved) return disp;
+    const int sl = disp / (2 * d.nr), r = disp % (2 * d.nr), hi = r >= d.nr, k = r - hi * d.nr;
+    return 4 * ((k >> 1) * d.lpc + sl) + 2 * hi + (k & 1);
+}
+// fills lpc, nr, lpc_shift, interleaved from D (sgm.cu)
+void set_cell_order(Dims &d);
 
 __host__ __device__ inline int view_rows(const Dims &d, int v) { return v < 2 ? d.Hp : d.Wp; }
 __host__ __device__ inline int view_cols(const Dims &d, int v) { return v < 2 ? d.Wp : d.Hp; }

@@ -442,6 +442,12 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
     if (i >= d.Hp) return;
     constexpr int NKC = NK > 0 ? NK : 16;
     bool overflow = false;
+    // The lane writes bytes lane + 32k of the cell; which disparity that is depends on the cell's byte order (Dims,
+    // common.cuh). It separates into a lane part and a per-k part (lpc is 8 or 16, so a block of 32 bytes = 8 words never
+    // straddles a row of the word matrix): d = dl + dku(k). Within a k the 32 lanes still read 32 distinct 8-byte census
+    // codes whose indices cover every residue mod 16 twice (once per half warp): conflict-free like the natural order.
+    const int dl = d.interleaved ? 2 * d.nr * (lane >> 2) + (lane & 1) + d.nr * ((lane >> 1) & 1) : lane;
+    auto dku = [&](int k) { return d.interleaved ? 2 * d.nr * ((8 * k) & (d.lpc - 1)) + 2 * ((8 * k) >> d.lpc_shift) : 32 * k; };
 #pragma unroll 1
     for (int lj = 0; lj < T; lj++) {
         const int j = j0 + lj;
@@ -461,11 +467,11 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
             if (rv >= 3 && rv < hv - 2 && cc >= D - 1) {
                 const unsigned long long c1 = sc1[(v * T + li) * T + lj];
                 const unsigned c1lo = (unsigned)c1, c1hi = (unsigned)(c1 >> 32);
-                const unsigned long long *p = line - lane;
+                const unsigned long long *p = line - dl;
 #pragma unroll
                 for (int k = 0; k < NKC; k++) {
                     if (NK > 0 || lane + 32 * k < D) {
-                        const uint2 x = *reinterpret_cast<const uint2 *>(p - 32 * k);
+                        const uint2 x = *reinterpret_cast<const uint2 *>(p - dku(k));
                         acc[k] += __popc(x.x ^ c1lo) + __popc(x.y ^ c1hi);
                     }
                 }
@@ -477,8 +483,8 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
                 if (popc_row) c1 = sc1[(v * T + li) * T + lj];
 #pragma unroll 1
                 for (int k = 0; k < NKC; k++) {
-                    const int dd = lane + 32 * k;
-                    if (dd >= D) break;
+                    if (lane + 32 * k >= D) break;
+                    const int dd = dl + dku(k);
                     unsigned cst;
                     if (rv < 3) cst = kInvalidCost;
                     else if (!popc_row) cst = 0;

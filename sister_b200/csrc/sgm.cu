@@ -32,13 +32,34 @@
 // scattered runs of 192-byte cells), not by issue slots: halving the instruction count, doubling the warps or
 // deepening the prefetch each moved it by less than 5 % (profiles/r01_ncu_v16_paths.txt).
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.cuh"
 #include "sgm_core.cuh"
 
 namespace sister {
 
-constexpr int kChainWarps = 8;    // warps per block (they share nothing)
+#ifndef SISTER_SGM_CHAIN_WARPS
+#define SISTER_SGM_CHAIN_WARPS 8
+#endif
+constexpr int kChainWarps = SISTER_SGM_CHAIN_WARPS;    // warps per block (they share nothing)
+// 24 resident warps per SM (80 registers) up to this many packed registers per lane when every lane is full, else 16
+#ifndef SISTER_SGM_FULL_NR20
+#define SISTER_SGM_FULL_NR20 0
+#endif
+#ifndef SISTER_SGM_FULL_NR32
+#define SISTER_SGM_FULL_NR32 0
+#endif
+#ifndef SISTER_SGM_NR24
+#define SISTER_SGM_NR24 8
+#endif
+#ifndef SISTER_SGM_FULL_NR24
+#define SISTER_SGM_FULL_NR24 12
+#endif
+constexpr int resident_warps(int NR, bool FULL)
+{
+    return (FULL && NR <= SISTER_SGM_FULL_NR32) ? 32 : (NR <= SISTER_SGM_NR24 || (FULL && NR <= SISTER_SGM_FULL_NR24)) ? 24 : (FULL && NR <= SISTER_SGM_FULL_NR20) ? 20 : 16;
+}
 
 // ---------------------------------------------------------------------------------------------- chain geometry
 
@@ -194,8 +215,8 @@ template <bool DIAG> __device__ __forceinline__ bool in_roi(const Cursor &c, con
 
 // KIND 0: r0 on an ordinary row; 1: r0 on the first line of a pass; 2: r1 / r2 / r3 (columns ride along in the
 // wrapped-diagonal loop, sj = 0 never wraps).
-template <int NR, int LPC, bool FULL, int KIND>
-__device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane, uint8_t *__restrict__ q_lane, const LaneInfo<NR, LPC, FULL> &li,
+template <int NR, int LPC, bool FULL, bool IL, int KIND>
+__device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane, const uint8_t *__restrict__ fused_pfl, uint8_t *__restrict__ q_lane, const LaneInfo<NR, LPC, FULL> &li,
                                           const Walk &wk, Cursor first, int nsteps, int valid_bytes,
                                           const uint8_t *state_in = nullptr, uint8_t *state_out = nullptr, bool starts_on_first_line = true)
 {
@@ -206,7 +227,7 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
     // every request is guarded by the step count)
 #pragma unroll
     for (int t = 0; t < kAhead; t++) {
-        load_cost<NR, FULL>(fused_lane + (long long)ld.off8 * 8, valid_bytes, buf[t]); // nsteps >= 12 (check_shape, sister_test_sgm)
+        load_cost<NR, LPC, FULL, IL>(fused_lane + (long long)ld.off8 * 8, valid_bytes, buf[t]); // nsteps >= 12 (check_shape, sister_test_sgm)
         advance<DIAG>(ld, wk); // nsteps > kAhead: ld now points at step kAhead
     }
     // the first line of a pass reads an invalid cost (255, census.cpp:76) as 0 (sgm.cpp:109,123,146); fused volumes
@@ -218,7 +239,7 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
     pf = ld;
 #pragma unroll 1
     for (int t = 0; t < kFar && kAhead + t < nsteps; t++) {
-        if (valid_bytes > 0) prefetch_l2(fused_lane + (long long)pf.off8 * 8);
+        if (valid_bytes > 0) prefetch_l2(fused_pfl + (long long)pf.off8 * 8);
         advance<DIAG>(pf, wk);
     }
     ChainState<NR> cs;
@@ -229,8 +250,8 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
     chain_set<NR, LPC, FULL>(cs, 0u, li);
     if (KIND == 2 && state_in) { // warp-uniform: the chain continues from the band before (Band)
         uint32_t w[NR / 2], a[NR];
-        load_cost<NR, FULL>(state_in, valid_bytes, w);
-        unpack_cost<NR>(w, a);
+        load_cost<NR, LPC, FULL, IL>(state_in, valid_bytes, w);
+        unpack_cost<NR, IL>(w, a);
         chain_resume<NR, LPC, FULL>(cs, a, li);
     }
     // one step: consume buffer u (step s), refill it with step s + kAhead (past the end of the chain the last cell is
@@ -241,11 +262,11 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
 #pragma unroll
             for (int k = 0; k < NR / 2; k++) buf[u][k] &= ~__vcmpeq4(buf[u][k], 0xFFFFFFFFu);
         }
-        unpack_cost<NR>(buf[u], c);
-        load_cost<NR, FULL>(fused_lane + (long long)ld.off8 * 8, valid_bytes, buf[u]);
+        unpack_cost<NR, IL>(buf[u], c);
+        load_cost<NR, LPC, FULL, IL>(fused_lane + (long long)ld.off8 * 8, valid_bytes, buf[u]);
         if (s + kAhead + 1 < nsteps) advance<DIAG>(ld, wk);
         if (s + kAhead + kFar < nsteps) {
-            if (FULL || valid_bytes > 0) prefetch_l2(fused_lane + (long long)pf.off8 * 8);
+            if (FULL || valid_bytes > 0) prefetch_l2(fused_pfl + (long long)pf.off8 * 8);
             advance<DIAG>(pf, wk);
         }
         uint8_t *dst = q_lane + (long long)st.off8 * 8;
@@ -258,24 +279,314 @@ __device__ __forceinline__ void run_chain(const uint8_t *__restrict__ fused_lane
         } else {
             chain_step<NR, LPC, FULL>(cs, c, li, q, off_next);
         }
-        if (wanted) store_q<NR, FULL>(dst, q, valid_bytes);
+        if (wanted) store_q<NR, LPC, FULL, IL>(dst, q, valid_bytes);
+    };
+    // The same step between border crossings and away from the chain's end, where all three cursors are plain arithmetic
+    // progressions: the load / prefetch addresses are fixed offsets from the store cursor, no wrap test, no end-of-chain
+    // guard, no border select in the renormalisation. Whether a step's cell can lie in the region of interest is
+    // warp-uniform (a section's chains sit on the same row -- KIND 2 -- or column -- KIND 0 -- at the same step): steps
+    // [w_lo, w_hi). A fast run never straddles one of those edges, so it either stores nothing (STORE = false) or
+    // stores under the per-lane column test only (KIND 2) / unconditionally (KIND 0). The kernel is bound by the ALU
+    // pipe; the general step costs about 20 more instructions of that pipe.
+    int w_lo, w_hi;
+    if constexpr (DIAG) {
+        w_lo = wk.si > 0 ? wk.r0 - first.i : first.i - (wk.r0 + (int)wk.nr - 1);
+        w_hi = wk.si > 0 ? wk.r0 + (int)wk.nr - first.i : first.i - wk.r0 + 1;
+    } else {
+        w_lo = wk.sj > 0 ? wk.c0 - first.j : first.j - (wk.c0 + (int)wk.nc - 1);
+        w_hi = wk.sj > 0 ? wk.c0 + (int)wk.nc - first.j : first.j - wk.c0 + 1;
+    }
+    const int ld_ahead = kAhead * wk.stride8, pf_ahead = (kAhead + kFar) * wk.stride8;
+    auto fast_step = [&](const int u, auto store_tag) {
+        constexpr bool STORE = decltype(store_tag)::value;
+        uint32_t c[NR], q[NR];
+        unpack_cost<NR, IL>(buf[u], c);
+        load_cost<NR, LPC, FULL, IL>(fused_lane + (long long)(st.off8 + ld_ahead) * 8, valid_bytes, buf[u]);
+        if (FULL || valid_bytes > 0) prefetch_l2(fused_pfl + (long long)(st.off8 + pf_ahead) * 8);
+        chain_step<NR, LPC, FULL>(cs, c, li, q);
+        if constexpr (STORE) {
+            uint8_t *dst = q_lane + (long long)st.off8 * 8;
+            if constexpr (DIAG) {
+                if ((unsigned)(st.j - wk.c0) < wk.nc) store_q<NR, LPC, FULL, IL>(dst, q, valid_bytes);
+                st.j += wk.sj;
+            } else {
+                store_q<NR, LPC, FULL, IL>(dst, q, valid_bytes);
+            }
+        }
+        st.off8 += wk.stride8;
     };
     int s0 = 0;
 #pragma unroll 1
-    for (; s0 + kAhead <= nsteps; s0 += kAhead) {
+    while (s0 + kAhead <= nsteps) {
+        int nfast = 0;
+        bool inside = false;
+        if constexpr (KIND != 1) {
+            // advances the store cursor can make before the one that crosses a border, the fewest over the warp's chains;
+            // the prefetch cursor runs kAhead + kFar steps ahead of it
+            int room = nsteps - s0 - (kAhead + kFar) - 1;
+            if constexpr (DIAG) {
+                const int tw = wk.sj > 0 ? wk.Wp - 1 - st.j : wk.sj < 0 ? st.j : 0x3FFFFFFF;
+                room = min(room, __reduce_min_sync(kFull, tw) - (kAhead + kFar));
+            }
+            inside = s0 >= w_lo && s0 < w_hi;
+            room = min(room, (s0 < w_lo ? w_lo : s0 < w_hi ? w_hi : 0x3FFFFFFF) - s0);
+            nfast = room >= 2 * kAhead ? room / kAhead : 0; // groups of kAhead steps
+        }
+        if (nfast > 0) {
+            if (inside) {
+#pragma unroll 1
+                for (int g = 0; g < nfast; g++) {
 #pragma unroll
-        for (int u = 0; u < kAhead; u++) step(u, s0 + u);
+                    for (int u = 0; u < kAhead; u++) fast_step(u, std::true_type{});
+                }
+                if constexpr (!DIAG) st.j += nfast * kAhead * wk.sj;
+            } else {
+#pragma unroll 1
+                for (int g = 0; g < nfast; g++) {
+#pragma unroll
+                    for (int u = 0; u < kAhead; u++) fast_step(u, std::false_type{});
+                }
+                st.j += nfast * kAhead * wk.sj;
+            }
+            st.i += nfast * kAhead * wk.si;
+            s0 += nfast * kAhead;
+            // the general step's cursors again: load at step s0 + kAhead, prefetch at s0 + kAhead + kFar (no crossing in between)
+            ld = st; ld.off8 += ld_ahead; ld.j += kAhead * wk.sj; ld.i += kAhead * wk.si;
+            pf = st; pf.off8 += pf_ahead; pf.j += (kAhead + kFar) * wk.sj; pf.i += (kAhead + kFar) * wk.si;
+        } else {
+#pragma unroll
+            for (int u = 0; u < kAhead; u++) step(u, s0 + u);
+            s0 += kAhead;
+        }
     }
 #pragma unroll
     for (int u = 0; u < kAhead - 1; u++)
         if (s0 + u < nsteps) step(u, s0 + u); // warp-uniform
-    if (KIND == 2 && state_out) store_q<NR, FULL>(state_out, cs.a, valid_bytes); // a <= P2 fits a byte
+    if (KIND == 2 && state_out) store_q<NR, LPC, FULL, IL>(state_out, cs.a, valid_bytes); // a <= P2 fits a byte
 }
 
-// grid ceil(chains / (kChainWarps * 32 / LPC)), block kChainWarps * 32, no shared memory
-template <int NR, int LPC, bool FULL>
-__global__ void __launch_bounds__(kChainWarps * 32, ((NR <= 8 || (FULL && NR <= 12)) ? 24 : 16) / kChainWarps) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, Roi roi, Band band, Sections sec, uint8_t *__restrict__ qvol, unsigned section_mask,
-                                                                                                             long long first_block)
+// ---- the same chain with the fused costs staged through a per-warp shared-memory ring (full lanes: D == 2 * NR * LPC).
+// The kernel is bound by the latency of its cost loads (stall sampling: long scoreboard on the first use of a loaded
+// cell), registers cap the lookahead of run_chain at 3 steps and more resident warps help more than more lookahead. Here
+// every step the warp copies the 32 / LPC cells of the step kRing - 1 ahead with 16-byte cp.async (cells are 16-byte
+// aligned, a warp step is 4 * NR chunks) into the ring slot it consumed one step ago and reads its own words of the
+// current slot back: no lookahead registers, a lookahead of kRing - 1 steps.
+#ifndef SISTER_SGM_RING
+#define SISTER_SGM_RING 8
+#endif
+constexpr int kRing = SISTER_SGM_RING;
+
+__device__ __forceinline__ void cp_async16(unsigned dst_s, const uint8_t *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_s), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(unsigned a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint2 lds64v(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint4 lds128v(unsigned a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v; }
+
+// the lane's NR / 2 words of its chain's cell in a ring slot (a = slot + the lane's first byte)
+template <int NR, int LPC, bool IL> __device__ __forceinline__ void ring_read(unsigned a, uint32_t (&w)[NR / 2])
+{
+    if constexpr (IL) {
+#pragma unroll
+        for (int k = 0; k < NR / 2; k++) w[k] = lds32(a + 4 * LPC * k);
+    } else if constexpr (NR % 8 == 0) {
+#pragma unroll
+        for (int k = 0; k < NR / 8; k++) { const uint4 v = lds128v(a + 16 * k); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+    } else if constexpr (NR % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < NR / 4; k++) { const uint2 v = lds64v(a + 8 * k); w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NR / 2; k++) w[k] = lds32(a + 4 * k);
+    }
+}
+
+template <int NR, int LPC, bool IL, int KIND>
+__device__ __forceinline__ void run_chain_ring(const uint8_t *__restrict__ fused, uint8_t *__restrict__ q_lane, const LaneInfo<NR, LPC, true> &li, const Walk &wk,
+                                               Cursor first, int nsteps, unsigned ring_s, int lane, const uint8_t *state_in = nullptr,
+                                               uint8_t *state_out = nullptr, bool starts_on_first_line = true)
+{
+    constexpr bool DIAG = KIND == 2;
+    constexpr int D = 2 * NR * LPC;    // bytes per cell
+    constexpr int CH = D / 16;         // 16-byte chunks per cell
+    constexpr int NCH = 4 * NR;        // chunks per warp and step: 32 / LPC cells
+    constexpr int NCP = (NCH + 31) / 32;
+    constexpr int SS = (32 / LPC) * D; // bytes per ring slot
+    constexpr int R = kRing, A = R - 1;
+    constexpr int U = 2;               // steps per trip of the main loops
+    // copy cursors: chunk g = lane + 32 n of the warp step belongs to the cell of chain g / CH
+    Cursor cp[NCP];
+    const uint8_t *cp_src[NCP];
+    unsigned cp_dst[NCP];
+    int cp_stride8[NCP];
+    bool cp_on[NCP];
+#pragma unroll
+    for (int n = 0; n < NCP; n++) {
+        const int g = lane + 32 * n;
+        cp_on[n] = g < NCH;
+        const int c = cp_on[n] ? g / CH : 0;
+        cp[n].off8 = __shfl_sync(kFull, first.off8, c * LPC);
+        cp[n].i = __shfl_sync(kFull, first.i, c * LPC);
+        cp[n].j = __shfl_sync(kFull, first.j, c * LPC);
+        cp_src[n] = fused + (g - c * CH) * 16;
+        cp_dst[n] = ring_s + g * 16;
+        // the two first-line chains of a warp (KIND 1) run in opposite directions: the stride is that of the chain copied for
+        cp_stride8[n] = __shfl_sync(kFull, wk.stride8, c * LPC);
+    }
+    // copy the cells of step t (where the copy cursors stand) into the slot at byte offset slot_off, move on
+    auto copy_step = [&](const int t, const unsigned slot_off) {
+        if (t < nsteps) {
+#pragma unroll
+            for (int n = 0; n < NCP; n++)
+                if (cp_on[n]) cp_async16(cp_dst[n] + slot_off, cp_src[n] + (long long)cp[n].off8 * 8);
+            if (t + 1 < nsteps) {
+#pragma unroll
+                for (int n = 0; n < NCP; n++) {
+                    if constexpr (DIAG) advance<DIAG>(cp[n], wk); // one section, one walk
+                    else cp[n].off8 += cp_stride8[n];
+                }
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int t = 0; t < A; t++) copy_step(t, t * SS);
+    const unsigned rd_lane = ring_s + (lane / LPC) * D + li.template cell_offset<IL>();
+    unsigned rd_off = 0, wr_off = A * SS; // slot of the current step / of the step A ahead (the one consumed last)
+    Cursor st = first;
+    ChainState<NR> cs;
+    uint32_t mm = 0;          // KIND 1: minimum of the truncated state
+    // initial state as in run_chain
+    chain_set<NR, LPC, true>(cs, 0u, li);
+    if (KIND == 2 && state_in) { // warp-uniform: the chain continues from the band before (Band)
+        uint32_t w[NR / 2], a[NR];
+        load_cost<NR, LPC, true, IL>(state_in, 2 * NR, w);
+        unpack_cost<NR, IL>(w, a);
+        chain_resume<NR, LPC, true>(cs, a, li);
+    }
+    // the slot of the current step has landed (every lane waits for its own copies, then the warp meets); read it
+    auto fetch = [&](uint32_t (&c)[NR], const bool zero_invalid) {
+        cp_async_wait<A - 1>();
+        __syncwarp();
+        uint32_t w[NR / 2];
+        ring_read<NR, LPC, IL>(rd_lane + rd_off, w);
+        // the first line of a pass reads an invalid cost (255, census.cpp:76) as 0 (sgm.cpp:109,123,146); fused volumes
+        // never hold 255 (match.cu), the raw two-view volume of sister_stereo does
+        if (zero_invalid) {
+#pragma unroll
+            for (int k = 0; k < NR / 2; k++) w[k] &= ~__vcmpeq4(w[k], 0xFFFFFFFFu);
+        }
+        unpack_cost<NR, IL>(w, c);
+    };
+    auto turn = [&]() {
+        wr_off = rd_off;
+        rd_off = rd_off + SS == R * SS ? 0u : rd_off + SS;
+    };
+    auto step = [&](const int s) {
+        uint32_t c[NR], q[NR];
+        fetch(c, KIND == 1 || (KIND == 2 && starts_on_first_line && s == 0));
+        copy_step(s + A, wr_off);
+        turn();
+        uint8_t *dst = q_lane + (long long)st.off8 * 8;
+        const bool wanted = in_roi<DIAG>(st, wk);
+        const bool off_next = advance<DIAG>(st, wk); // KIND 2: the next cell follows a border crossing
+        if constexpr (KIND == 1) {
+            first_line_step<NR, LPC, true>(cs.a, cs.b, mm, c, li, s == 0, q);
+        } else if constexpr (KIND == 0) {
+            chain_step<NR, LPC, true>(cs, c, li, q);
+        } else {
+            chain_step<NR, LPC, true>(cs, c, li, q, off_next);
+        }
+        if (wanted) store_q<NR, LPC, true, IL>(dst, q, 2 * NR);
+    };
+    // The same step between border crossings and away from the chain's end, where every cursor is a plain arithmetic
+    // progression: no wrap test, no end-of-chain guard, no border select in the renormalisation. Whether a step's cell can
+    // lie in the region of interest is warp-uniform (a section's chains sit on the same row -- KIND 2 -- or column --
+    // KIND 0 -- at the same step): steps [w_lo, w_hi). A fast run never straddles one of those edges, so it either stores
+    // nothing or stores under the per-lane column test only (KIND 2) / unconditionally (KIND 0).
+    int w_lo, w_hi;
+    if constexpr (DIAG) {
+        w_lo = wk.si > 0 ? wk.r0 - first.i : first.i - (wk.r0 + (int)wk.nr - 1);
+        w_hi = wk.si > 0 ? wk.r0 + (int)wk.nr - first.i : first.i - wk.r0 + 1;
+    } else {
+        w_lo = wk.sj > 0 ? wk.c0 - first.j : first.j - (wk.c0 + (int)wk.nc - 1);
+        w_hi = wk.sj > 0 ? wk.c0 + (int)wk.nc - first.j : first.j - wk.c0 + 1;
+    }
+    auto fast_step = [&](auto store_tag) {
+        constexpr bool STORE = decltype(store_tag)::value;
+        uint32_t c[NR], q[NR];
+        fetch(c, false);
+#pragma unroll
+        for (int n = 0; n < NCP; n++) {
+            if (cp_on[n]) cp_async16(cp_dst[n] + wr_off, cp_src[n] + (long long)cp[n].off8 * 8);
+            cp[n].off8 += cp_stride8[n];
+        }
+        cp_async_commit();
+        turn();
+        chain_step<NR, LPC, true>(cs, c, li, q);
+        if constexpr (STORE) {
+            uint8_t *dst = q_lane + (long long)st.off8 * 8;
+            if constexpr (DIAG) {
+                if ((unsigned)(st.j - wk.c0) < wk.nc) store_q<NR, LPC, true, IL>(dst, q, 2 * NR);
+                st.j += wk.sj;
+            } else {
+                store_q<NR, LPC, true, IL>(dst, q, 2 * NR);
+            }
+        }
+        st.off8 += wk.stride8;
+    };
+    int s0 = 0;
+#pragma unroll 1
+    while (s0 + U <= nsteps) {
+        int nfast = 0;
+        bool inside = false;
+        if constexpr (KIND != 1) {
+            // advances the store cursor can make before the one that crosses a border, the fewest over the warp's chains;
+            // the copy cursors run A steps ahead of it and must not reach the chain's last cell either
+            int room = nsteps - s0 - A - 1;
+            if constexpr (DIAG) {
+                const int tw = wk.sj > 0 ? wk.Wp - 1 - st.j : wk.sj < 0 ? st.j : 0x3FFFFFFF;
+                room = min(room, __reduce_min_sync(kFull, tw) - A);
+            }
+            inside = s0 >= w_lo && s0 < w_hi;
+            room = min(room, (s0 < w_lo ? w_lo : s0 < w_hi ? w_hi : 0x3FFFFFFF) - s0);
+            nfast = (room >= 2 * U && s0 > 0) ? room / U : 0; // trips of U steps; step 0 is special (first line)
+        }
+        if (nfast > 0) {
+            if (inside) {
+#pragma unroll 1
+                for (int g = 0; g < nfast; g++) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) fast_step(std::true_type{});
+                }
+                if constexpr (!DIAG) st.j += nfast * U * wk.sj;
+            } else {
+#pragma unroll 1
+                for (int g = 0; g < nfast; g++) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) fast_step(std::false_type{});
+                }
+                st.j += nfast * U * wk.sj;
+            }
+            st.i += nfast * U * wk.si;
+#pragma unroll
+            for (int n = 0; n < NCP; n++) { cp[n].j += nfast * U * wk.sj; cp[n].i += nfast * U * wk.si; }
+            s0 += nfast * U;
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) step(s0 + u);
+            s0 += U;
+        }
+    }
+    if (s0 < nsteps) step(s0); // warp-uniform
+    cp_async_wait<0>();
+    if (KIND == 2 && state_out) store_q<NR, LPC, true, IL>(state_out, cs.a, 2 * NR); // a <= P2 fits a byte
+}
+
+// grid ceil(chains / (kChainWarps * 32 / LPC)), block kChainWarps * 32, dynamic shared memory: the warps' cost rings (full lanes)
+template <int NR, int LPC, bool FULL, bool IL>
+__global__ void __launch_bounds__(kChainWarps * 32, resident_warps(NR, FULL) / kChainWarps) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, Roi roi, Band band, Sections sec, uint8_t *__restrict__ qvol, unsigned section_mask,
+                                                                                                             long long first_block, unsigned one)
 {
     constexpr int CPW = 32 / LPC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -290,28 +601,40 @@ __global__ void __launch_bounds__(kChainWarps * 32, ((NR <= 8 || (FULL && NR <= 
     if (kind < 0) return; // warp-uniform: sections are padded to whole warps
     if (!((section_mask >> section) & 1u)) return; // band pipelines run the sections in separate launches
     const int D = d.D, Wp = d.Wp, D8 = D >> 3;
-    const uint8_t *fused_lane = fused + li.sl * 2 * NR;
-    uint8_t *q_lane = qvol + (size_t)ch.vol * (size_t)d.cells + li.sl * 2 * NR;
+    const uint8_t *fused_lane = fused + li.template cell_offset<IL>();
+    uint8_t *q_lane = qvol + (size_t)ch.vol * (size_t)d.cells + li.template cell_offset<IL>();
     const int valid_bytes = li.valid_bytes(D); // bytes of this lane inside the cell
     // per-lane constants derived from %tid: pin them in registers, otherwise ptxas re-derives them inside every step
     opaque(li.up_mask); opaque(li.dn_mask);
+    li.one = one; // a kernel argument: the only 1 neither nvvm nor ptxas can fold (add_fma)
+    // the prefetch requests of a chain's lanes cover the whole cell whatever its byte order
+    const uint8_t *fused_pfl = fused + li.sl * 2 * NR;
     opaque_ptr(fused_lane); opaque_ptr(q_lane);
+    if constexpr (IL) opaque_ptr(fused_pfl);
+    else fused_pfl = fused_lane;
     Walk wk;
     wk.stride8 = (ch.si * Wp + ch.sj) * D8;
     wk.wrapfix8 = -ch.sj * Wp * D8;
+    if (section_mask >> 31) wk.stride8 = wk.wrapfix8 = 0; // measurement aid (SISTER_DEBUG_PATH_KINDS bit 3): every step on the chain's first cell
     wk.si = ch.si; wk.sj = ch.sj; wk.enter = ch.enter; wk.Wp = Wp;
     wk.r0 = roi.r0; wk.c0 = roi.c0; wk.nr = (unsigned)(roi.r1 - roi.r0); wk.nc = (unsigned)(roi.c1 - roi.c0);
     Cursor first;
     first.off8 = (ch.i * Wp + ch.j) * D8;
     first.i = ch.i;
     first.j = ch.j;
-    if (kind == 1) run_chain<NR, LPC, FULL, 1>(fused_lane, q_lane, li, wk, first, nsteps, valid_bytes);
-    else if (kind == 0) run_chain<NR, LPC, FULL, 0>(fused_lane, q_lane, li, wk, first, nsteps, valid_bytes);
-    else {
-        const int p = (section - 3) / 3;
-        const uint8_t *sin = (imports && band.in[p]) ? band.in[p] + state_off + li.sl * 2 * NR : nullptr;
-        uint8_t *sout = (exports && band.out[p]) ? band.out[p] + state_off + li.sl * 2 * NR : nullptr;
-        run_chain<NR, LPC, FULL, 2>(fused_lane, q_lane, li, wk, first, nsteps, valid_bytes, sin, sout, !imports);
+    const int p = kind == 2 ? (section - 3) / 3 : 0;
+    const uint8_t *sin = (kind == 2 && imports && band.in[p]) ? band.in[p] + state_off + li.template cell_offset<IL>() : nullptr;
+    uint8_t *sout = (kind == 2 && exports && band.out[p]) ? band.out[p] + state_off + li.template cell_offset<IL>() : nullptr;
+    if constexpr (FULL) {
+        extern __shared__ __align__(16) unsigned char ring_raw[];
+        const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring_raw) + warp * (kRing * (32 / LPC) * 2 * NR * LPC);
+        if (kind == 1) run_chain_ring<NR, LPC, IL, 1>(fused, q_lane, li, wk, first, nsteps, ring_s, lane);
+        else if (kind == 0) run_chain_ring<NR, LPC, IL, 0>(fused, q_lane, li, wk, first, nsteps, ring_s, lane);
+        else run_chain_ring<NR, LPC, IL, 2>(fused, q_lane, li, wk, first, nsteps, ring_s, lane, sin, sout, !imports);
+    } else {
+        if (kind == 1) run_chain<NR, LPC, FULL, IL, 1>(fused_lane, fused_pfl, q_lane, li, wk, first, nsteps, valid_bytes);
+        else if (kind == 0) run_chain<NR, LPC, FULL, IL, 0>(fused_lane, fused_pfl, q_lane, li, wk, first, nsteps, valid_bytes);
+        else run_chain<NR, LPC, FULL, IL, 2>(fused_lane, fused_pfl, q_lane, li, wk, first, nsteps, valid_bytes, sin, sout, !imports);
     }
 }
 
@@ -323,7 +646,8 @@ __device__ __forceinline__ uint2 ldg8(const uint8_t *p) { return __ldg(reinterpr
 // convertTo(CV_16UC1), crop Rect(D, D, W, H) and * 255 with saturation (hpp:111-118).
 // Eight lanes per pixel, each lane owns 8-byte chunks sub, sub + 8, ... of the pixel's D bytes in all nine volumes.
 // grid-stride over groups of 4 pixels per warp.
-__global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ fused, const uint8_t *__restrict__ qvol, Dims d, Roi roi,
+template <bool IL>
+__global__ void __launch_bounds__(256, 6) k_sgm_final(const uint8_t *__restrict__ fused, const uint8_t *__restrict__ qvol, Dims d, Roi roi,
                                                    uint16_t *__restrict__ sum, int16_t *__restrict__ raw_disp, uint16_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
@@ -344,8 +668,15 @@ __global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ f
         if (live) {
             const size_t off0 = (size_t)pix * D;
             for (int chunk = sub; chunk < nchunk; chunk += 8) {
-                const int d0 = chunk * 8;
-                const size_t off = off0 + d0;
+                const size_t off = off0 + chunk * 8;
+                // disparities of the chunk's four byte pairs: db + (k & 1) * s1 + (k >> 1) * s2 and the one after it
+                // (natural order: consecutive; lane-interleaved cell, common.cuh: words (t, sl), (t, sl + 1))
+                int db = chunk * 8, s1 = 2, s2 = 4;
+                if constexpr (IL) {
+                    const int word = chunk * 2;
+                    db = (word & (d.lpc - 1)) * 2 * d.nr + 2 * (word >> d.lpc_shift);
+                    s1 = d.nr; s2 = 2 * d.nr;
+                }
                 const uint2 cc = ldg8(fused + off);
                 uint2 qq[8];
 #pragma unroll
@@ -355,7 +686,7 @@ __global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ f
                 uint32_t w[2][4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) { w[0][k] = qq[2 * k].x + qq[2 * k + 1].x; w[1][k] = qq[2 * k].y + qq[2 * k + 1].y; }
-                uint32_t S[4]; // 8 cells as packed u16: S[0] = d0, d0+1; S[1] = d0+2, d0+3; ...
+                uint32_t S[4]; // 8 cells as packed u16: S[k] = bytes 2k, 2k + 1 of the chunk
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const uint32_t cw = h ? cc.y : cc.x;
@@ -364,10 +695,10 @@ __global__ void __launch_bounds__(256) k_sgm_final(const uint8_t *__restrict__ f
                     for (int k = 0; k < 4; k++) { lo += __byte_perm(w[h][k], 0u, 0x4140); hi += __byte_perm(w[h][k], 0u, 0x4342); }
                     S[2 * h] = lo; S[2 * h + 1] = hi;
                 }
-                if (sum) *reinterpret_cast<uint4 *>(sum + off) = make_uint4(S[0], S[1], S[2], S[3]);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const int da = d0 + 2 * k;
+                    const int da = db + (k & 1) * s1 + (k >> 1) * s2;
+                    if (sum) *reinterpret_cast<uint32_t *>(sum + off0 + da) = S[k]; // the test tap is in natural order
                     if (da <= dmax) best = min(best, ((S[k] & 0xFFFFu) << 16) | (unsigned)da);
                     if (da + 1 <= dmax) best = min(best, (S[k] & 0xFFFF0000u) | (unsigned)(da + 1));
                 }
@@ -413,6 +744,22 @@ void launch_wta_right_sum(const uint16_t *sum, const Dims &d, int16_t *outR, cud
 
 // ---------------------------------------------------------------------------------------------- launch
 
+// How a chain is spread over lanes, and with it the byte order of a cell (common.cuh): disparities per lane = 2 * nr, nr
+// even, chosen so that D fits in lpc lanes. Crop-only the kernel is bound by the ALU pipe with few chains left:
+// measured on B200 at D = 192, two chains per warp (twice the warps) beat four chains per warp by 20 %.
+void set_cell_order(Dims &d)
+{
+    static int lpc8_max = -1; // measurement aid: SISTER_DEBUG_LPC8_MAXD=<largest D that runs four chains per warp>
+    if (lpc8_max < 0) { const char *e = getenv("SISTER_DEBUG_LPC8_MAXD"); lpc8_max = e ? atoi(e) : 128; }
+    d.lpc = (d.D <= lpc8_max && d.D <= 192) ? 8 : 16;
+    d.lpc_shift = d.lpc == 8 ? 3 : 4;
+    d.nr = 2 * ((d.D + 4 * d.lpc - 1) / (4 * d.lpc));
+    // interleave when the lanes are exactly full and k_fuse's shared-memory reads stay conflict-free in that order: the
+    // codes a half warp reads are 2nr apart in groups of four lanes, distinct modulo 16 iff nr = 2 (mod 4): D = 32, 96
+    // (lpc 8), 64, 192, 320, 448 (lpc 16)
+    d.interleaved = (d.D == 2 * d.lpc * d.nr && d.nr % 4 == 2) ? 1 : 0;
+}
+
 // measurement aid: SISTER_DEBUG_PATH_KINDS=<bit mask of chain kinds to run> (results are then incomplete)
 static unsigned debug_section_mask()
 {
@@ -420,12 +767,12 @@ static unsigned debug_section_mask()
     if (m < 0) {
         const char *e = getenv("SISTER_DEBUG_PATH_KINDS");
         const int kinds = e ? atoi(e) & 7 : 7;
-        m = ((kinds & 2) ? 0x001 : 0) | ((kinds & 1) ? 0x006 : 0) | ((kinds & 4) ? 0x1F8 : 0);
+        m = ((kinds & 2) ? 0x001 : 0) | ((kinds & 1) ? 0x006 : 0) | ((kinds & 4) ? 0x1F8 : 0) | ((e && (atoi(e) & 8)) ? (int)0x80000000u : 0);
     }
     return (unsigned)m;
 }
 
-template <int NR, int LPC, bool FULL>
+template <int NR, int LPC, bool FULL, bool IL>
 static void launch_paths(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol, cudaStream_t st)
 {
     constexpr int CPW = 32 / LPC;
@@ -437,21 +784,28 @@ static void launch_paths(const uint8_t *fused, const Dims &d, const Roi &roi, co
     if (k0 >= k1) return;
     const long long per_block = (long long)kChainWarps * CPW;
     const long long first_block = sec.o[k0] / per_block, n = sec.o[k1] - first_block * per_block;
-    k_sgm_paths<NR, LPC, FULL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, 0, st>>>(fused, d, roi, band, sec, qvol, section_mask,
-                                                                                                       first_block);
+    const size_t smem = FULL ? (size_t)kChainWarps * kRing * CPW * d.D : 0; // the cost ring of run_chain_ring
+    if (smem > 48 * 1024) {
+        static bool attr_done = false; // per instantiation
+        if (!attr_done) { cudaFuncSetAttribute(k_sgm_paths<NR, LPC, FULL, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+    }
+    k_sgm_paths<NR, LPC, FULL, IL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, smem, st>>>(fused, d, roi, band, sec, qvol, section_mask,
+                                                                                                       first_block, 1u);
 }
 
 template <int LPC, int NRMAX>
 static void launch_paths_lpc(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol, cudaStream_t st)
 {
-    // disparities per lane = 2 * NR, NR even, chosen so that D fits in LPC lanes
-    const int nr = 2 * ((d.D + 4 * LPC - 1) / (4 * LPC));
+    const int nr = d.nr;
     const bool full = d.D == 2 * LPC * nr;
 #define SISTER_PATHS_CASE(N)                                                                    \
     case N:                                                                                     \
         if constexpr (N <= NRMAX) {                                                             \
-            if (full) launch_paths<N, LPC, true>(fused, d, roi, band, section_mask, qvol, st);                           \
-            else launch_paths<N, LPC, false>(fused, d, roi, band, section_mask, qvol, st);                               \
+            if constexpr (N % 4 == 2) {                                                         \
+                if (d.interleaved) { launch_paths<N, LPC, true, true>(fused, d, roi, band, section_mask, qvol, st); break; } \
+            }                                                                                   \
+            if (full) launch_paths<N, LPC, true, false>(fused, d, roi, band, section_mask, qvol, st);                    \
+            else launch_paths<N, LPC, false, false>(fused, d, roi, band, section_mask, qvol, st);                        \
         }                                                                                       \
         break;
     switch (nr) {
@@ -472,12 +826,8 @@ static Roi make_roi(const Dims &d, bool full_frame)
 static void launch_paths_any(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol,
                              cudaStream_t st)
 {
-    // Whole-frame the kernel is bound by DRAM, crop-only by the ALU pipe with few chains left: measured on B200 at D = 192
-    // two chains per warp (twice the warps) beat four chains per warp by 4 % / 20 %.
-    static int lpc8_max = -1; // measurement aid: SISTER_DEBUG_LPC8_MAXD=<largest D that runs four chains per warp>
-    if (lpc8_max < 0) { const char *e = getenv("SISTER_DEBUG_LPC8_MAXD"); lpc8_max = e ? atoi(e) : 128; }
-    if (d.D <= lpc8_max && d.D <= 192) launch_paths_lpc<8, 12>(fused, d, roi, band, section_mask, qvol, st); // four chains per warp
-    else launch_paths_lpc<16, 16>(fused, d, roi, band, section_mask, qvol, st);                             // two (D <= 512, check_shape)
+    if (d.lpc == 8) launch_paths_lpc<8, 12>(fused, d, roi, band, section_mask, qvol, st); // four chains per warp
+    else launch_paths_lpc<16, 16>(fused, d, roi, band, section_mask, qvol, st);           // two (D <= 512, check_shape)
 }
 
 static void launch_final(const uint8_t *fused, const uint8_t *qvol, const Dims &d, const Roi &roi, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
@@ -487,7 +837,8 @@ static void launch_final(const uint8_t *fused, const uint8_t *qvol, const Dims &
     if (groups <= 0) return;
     long long blocks = (groups + 7) / 8;
     if (blocks > 148LL * 64) blocks = 148LL * 64;
-    k_sgm_final<<<(unsigned)blocks, 256, 0, st>>>(fused, qvol, d, roi, sum, raw_disp, out);
+    if (d.interleaved) k_sgm_final<true><<<(unsigned)blocks, 256, 0, st>>>(fused, qvol, d, roi, sum, raw_disp, out);
+    else k_sgm_final<false><<<(unsigned)blocks, 256, 0, st>>>(fused, qvol, d, roi, sum, raw_disp, out);
 }
 
 void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, uint8_t *qvol, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
