@@ -31,8 +31,13 @@
 // kFar steps beyond that. On B200 the path kernel is bound by DRAM (about 5 TB/s of mixed reads and writes in
 // scattered runs of 192-byte cells), not by issue slots: halving the instruction count, doubling the warps or
 // deepening the prefetch each moved it by less than 5 % (profiles/r01_ncu_v16_paths.txt).
+#include <algorithm>
 #include <cstdlib>
+#include <initializer_list>
+#include <map>
+#include <mutex>
 #include <type_traits>
+#include <vector>
 
 #include "kernels.cuh"
 #include "sgm_core.cuh"
@@ -586,7 +591,7 @@ __device__ __forceinline__ void run_chain_ring(const uint8_t *__restrict__ fused
 // grid ceil(chains / (kChainWarps * 32 / LPC)), block kChainWarps * 32, dynamic shared memory: the warps' cost rings (full lanes)
 template <int NR, int LPC, bool FULL, bool IL>
 __global__ void __launch_bounds__(kChainWarps * 32, resident_warps(NR, FULL) / kChainWarps) k_sgm_paths(const uint8_t *__restrict__ fused, Dims d, Roi roi, Band band, Sections sec, uint8_t *__restrict__ qvol, unsigned section_mask,
-                                                                                                             long long first_block, unsigned one)
+                                                                                                             const int *__restrict__ warp_order, int n_warps, unsigned one)
 {
     constexpr int CPW = 32 / LPC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -596,10 +601,12 @@ __global__ void __launch_bounds__(kChainWarps * 32, resident_warps(NR, FULL) / k
     int nsteps = 0, section = 0;
     long long state_off = 0;
     bool imports, exports;
-    const int kind = chain_decode(d, roi, band, sec, ((first_block + blockIdx.x) * kChainWarps + warp) * CPW + lane / LPC, ch, nsteps, section,
-                                  state_off, imports, exports);
-    if (kind < 0) return; // warp-uniform: sections are padded to whole warps
-    if (!((section_mask >> section) & 1u)) return; // band pipelines run the sections in separate launches
+    const int w = blockIdx.x * kChainWarps + warp;
+    if (w >= n_warps) return;
+    // warp_order[w]: which CPW consecutive chains (of the padded numbering of Sections) this warp runs
+    const int kind = chain_decode(d, roi, band, sec, (long long)__ldg(warp_order + w) * CPW + lane / LPC, ch, nsteps, section, state_off, imports,
+                                  exports);
+    if (kind < 0) return; // cannot happen: the table only holds warps of the requested sections
     const int D = d.D, Wp = d.Wp, D8 = D >> 3;
     const uint8_t *fused_lane = fused + li.template cell_offset<IL>();
     uint8_t *q_lane = qvol + (size_t)ch.vol * (size_t)d.cells + li.template cell_offset<IL>();
@@ -772,25 +779,77 @@ static unsigned debug_section_mask()
     return (unsigned)m;
 }
 
+// The order warps are handed out in (blocks take kChainWarps consecutive warps, the grid is dispatched in block order).
+// Sections differ in cost per step and in length, and the three column / diagonal paths of a pass re-read each row of C
+// within a window of steps only if they advance at the same rate on every SM. So the warps of the sections that run
+// together are INTERLEAVED in proportion to the sections' sizes -- every block, hence every SM, gets the same mix -- in
+// two groups: first the row chains (the longest) with pass 0, then pass 1, which mostly forms the second wave of blocks.
+// Built once per launch geometry and kept on the device.
+struct WarpOrder {
+    int *dev = nullptr;
+    int n = 0;
+};
+static const WarpOrder &warp_order_for(const Sections &sec, unsigned section_mask, int cpw)
+{
+    struct Key {
+        long long o[10];
+        unsigned mask;
+        int cpw, device;
+        bool operator<(const Key &b) const
+        {
+            for (int k = 0; k < 10; k++) if (o[k] != b.o[k]) return o[k] < b.o[k];
+            if (mask != b.mask) return mask < b.mask;
+            if (cpw != b.cpw) return cpw < b.cpw;
+            return device < b.device;
+        }
+    };
+    static std::map<Key, WarpOrder> cache;
+    static std::mutex mu;
+    Key key;
+    for (int k = 0; k < 10; k++) key.o[k] = sec.o[k];
+    key.mask = section_mask & 0x1FFu; key.cpw = cpw;
+    cudaGetDevice(&key.device);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    std::vector<int> order;
+    auto merge = [&](std::initializer_list<int> group) {
+        struct Item { double pos; int section, slot; };
+        std::vector<Item> items;
+        for (int k : group) {
+            if (!((section_mask >> k) & 1u)) continue;
+            const int nw = (int)((sec.o[k + 1] - sec.o[k]) / cpw);
+            for (int w = 0; w < nw; w++) items.push_back({(w + 0.5) / nw, k, (int)(sec.o[k] / cpw) + w});
+        }
+        std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.pos < b.pos; });
+        for (const Item &i : items) order.push_back(i.slot);
+    };
+    merge({0});
+    merge({1, 2, 3, 4, 5});
+    merge({6, 7, 8});
+    WarpOrder wo;
+    wo.n = (int)order.size();
+    if (wo.n > 0) {
+        cudaMalloc((void **)&wo.dev, order.size() * sizeof(int));
+        cudaMemcpy(wo.dev, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    return cache.emplace(key, wo).first->second;
+}
+
 template <int NR, int LPC, bool FULL, bool IL>
 static void launch_paths(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol, cudaStream_t st)
 {
     constexpr int CPW = 32 / LPC;
     const Sections sec = chain_sections(d, roi, band, CPW);
-    // launch only the span of chain indices the requested sections cover
-    int k0 = 0, k1 = 9;
-    while (k0 < 9 && (!((section_mask >> k0) & 1u) || sec.n[k0] == 0)) k0++;
-    while (k1 > k0 && (!((section_mask >> (k1 - 1)) & 1u) || sec.n[k1 - 1] == 0)) k1--;
-    if (k0 >= k1) return;
-    const long long per_block = (long long)kChainWarps * CPW;
-    const long long first_block = sec.o[k0] / per_block, n = sec.o[k1] - first_block * per_block;
+    const WarpOrder &wo = warp_order_for(sec, section_mask, CPW);
+    if (wo.n == 0) return;
     const size_t smem = FULL ? (size_t)kChainWarps * kRing * CPW * d.D : 0; // the cost ring of run_chain_ring
     if (smem > 48 * 1024) {
         static bool attr_done = false; // per instantiation
         if (!attr_done) { cudaFuncSetAttribute(k_sgm_paths<NR, LPC, FULL, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
     }
-    k_sgm_paths<NR, LPC, FULL, IL><<<(unsigned)((n + per_block - 1) / per_block), kChainWarps * 32, smem, st>>>(fused, d, roi, band, sec, qvol, section_mask,
-                                                                                                       first_block, 1u);
+    k_sgm_paths<NR, LPC, FULL, IL><<<(unsigned)((wo.n + kChainWarps - 1) / kChainWarps), kChainWarps * 32, smem, st>>>(fused, d, roi, band, sec, qvol,
+                                                                                                            section_mask, wo.dev, wo.n, 1u);
 }
 
 template <int LPC, int NRMAX>

@@ -45,15 +45,19 @@ template <int LPC> __device__ __forceinline__ uint32_t chain_min2(uint32_t m2)
     uint32_t v = __vmins2(m2, __byte_perm(m2, m2, 0x1032));
     if constexpr (LPC == 32) {
         return __reduce_min_sync(kFull, v);
-    } else if constexpr (LPC == 16 && SISTER_SGM_REDUX) {
-        // two chains per warp: two independent warp-wide reductions (each chain's lanes pass infinity to the other's), whose
-        // latencies overlap, instead of four dependent shuffle rounds -- the step's critical path is what bounds the kernel
-        // whenever an SM holds few warps (the tail of the grid). v holds the same value in both halves, so the unsigned
-        // 32-bit order is the 16-bit order.
-        const bool upper = (threadIdx.x & 16) != 0;
-        const uint32_t r0 = __reduce_min_sync(kFull, upper ? 0x7FFF7FFFu : v);
-        const uint32_t r1 = __reduce_min_sync(kFull, upper ? v : 0x7FFF7FFFu);
-        return upper ? r1 : r0;
+    } else if constexpr ((LPC == 16 && SISTER_SGM_REDUX) || (LPC == 8 && SISTER_SGM_REDUX >= 2)) {
+        // 32 / LPC chains per warp: one warp-wide reduction per chain (the other chains' lanes pass infinity), independent of
+        // each other so that their latencies overlap, instead of log2(LPC) dependent shuffle rounds -- the step's critical
+        // path is what bounds the kernel whenever an SM holds few warps (the tail of the grid). v holds the same value in
+        // both halves, so the unsigned 32-bit order is the 16-bit order.
+        const int cid = (threadIdx.x & 31) / LPC;
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 32 / LPC; k++) {
+            const uint32_t m = __reduce_min_sync(kFull, cid == k ? v : 0x7FFF7FFFu);
+            r = cid == k ? m : r;
+        }
+        return r;
     } else {
 #pragma unroll
         for (int o = 1; o < LPC; o <<= 1) v = __vmins2(v, __shfl_xor_sync(kFull, v, o));
