@@ -73,16 +73,27 @@ void launch_prep(const uint8_t *in, size_t view_stride, int row_stride, int chan
 
 // ---------------------------------------------------------------------------------------------- census
 
-constexpr int kCenTileW = 32, kCenTileH = 8;
-constexpr int kCenHaloL = 5, kCenHaloR = 4, kCenHaloV = 3; // cols c-5..c+4 (the -5 is for the carry), rows r-3..r+3
-constexpr int kCenSmemW = kCenTileW + kCenHaloL + kCenHaloR + 3; // 44
-constexpr int kCenSmemH = kCenTileH + 2 * kCenHaloV;             // 14
+constexpr int kCenPx = 2;                        // horizontally adjacent pixels per thread (they share 8 of 9 window columns)
+constexpr int kCenTileW = 32 * kCenPx, kCenTileH = 8;
+constexpr int kCenOrg = 8;                       // staged column of the tile's first pixel
+constexpr int kCenWords = (kCenOrg + kCenTileW + 8) / 4; // staged columns c0-8 .. c0+71 as 32-bit words (needed: c0-5 .. c0+67)
+constexpr int kCenHaloV = 3;                     // rows r-3..r+3
+constexpr int kCenSmemH = kCenTileH + 2 * kCenHaloV; // 14
 
-// grid (ceil(wv/32), ceil(hv/8), 8), block (32, 8)
+// One census bit per two instructions: t = X(p - o) - X(p + o) is negative exactly when X(p + o) > X(p - o)
+// (census.cpp:24-28), and a funnel shift moves its sign bit into a group accumulator, first scanned bit first. The
+// offsets o and -o compare the same two pixels, so the window is walked by ROW PAIRS (r-3, r+3), (r-2, r+2), (r-1, r+1),
+// (r, r): a pair yields the 9 bits of its upper row (offsets y < 0) and the 9 bits of its lower row (y > 0) from the same
+// values, only two rows are live at a time, and a thread's two pixels share the loads (35 byte loads per pixel; the first
+// version kept the window in 73 registers and spent 64 loads + 77 ISETP + 65 SEL + 72 LOP3 / IMAD on the 63 bits). The
+// tile is staged with aligned 32-bit loads (the padded sizes are multiples of 4, hpp:35-41 + postprocess.cpp:18): a word
+// is inside the image or outside it as a whole; pixels that get a code never look outside (census.cpp:33-36), so outside
+// words are simply zero.
+// grid (ceil(wv/64), ceil(hv/8), 8), block (32, 8)
 __global__ void __launch_bounds__(256) k_census(const uint8_t *__restrict__ oriented, Dims d,
                                                 unsigned long long *__restrict__ census)
 {
-    __shared__ uint8_t T[kCenSmemH][kCenSmemW];
+    __shared__ __align__(16) uint8_t T[kCenSmemH][kCenWords * 4];
     const int o = blockIdx.z, v = o >> 1;
     const int hv = view_rows(d, v), wv = view_cols(d, v);
     const int r0 = blockIdx.y * kCenTileH, c0 = blockIdx.x * kCenTileW;
@@ -90,41 +101,81 @@ __global__ void __launch_bounds__(256) k_census(const uint8_t *__restrict__ orie
     const uint8_t *img = oriented + (size_t)o * d.px;
     unsigned long long *out = census + (size_t)o * d.px;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int e = tid; e < kCenSmemH * (kCenTileW + kCenHaloL + kCenHaloR); e += 256) {
-        int tr = e / (kCenTileW + kCenHaloL + kCenHaloR), tc = e % (kCenTileW + kCenHaloL + kCenHaloR);
-        int r = min(max(r0 - kCenHaloV + tr, 0), hv - 1);
-        int c = min(max(c0 - kCenHaloL + tc, 0), wv - 1);
-        T[tr][tc] = img[(size_t)r * wv + c];
+    for (int e = tid; e < kCenSmemH * kCenWords; e += 256) {
+        const int tr = e / kCenWords, tw = e % kCenWords;
+        const int r = r0 - kCenHaloV + tr, c = c0 - kCenOrg + 4 * tw;
+        uint32_t w = 0;
+        if (r >= 0 && r < hv && c >= 0 && c < wv) w = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)r * wv + c));
+        reinterpret_cast<uint32_t *>(&T[tr][0])[tw] = w;
     }
     __syncthreads();
-    const int r = r0 + threadIdx.y, c = c0 + threadIdx.x;
-    if (r >= hv || c >= wv) return;
-    unsigned long long code = 0;
-    if (r >= 3 && r <= hv - 4 && c >= 4 && c <= wv - 5) {
-        const int tr = threadIdx.y + kCenHaloV, tc = threadIdx.x + kCenHaloL;
-        unsigned carry;
-        if (c > 4) {
-            carry = T[tr + 3][tc + 3] > T[tr - 3][tc - 5]; // previous pixel (r, c-1): X(r+3, c-1+4) > X(r-3, c-1-4)
-        } else if (r > 3) {
-            // previous pixel in raster order is (r-1, wv-5): X(r+2, wv-1) > X(r-4, wv-9)
-            carry = img[(size_t)(r + 2) * wv + (wv - 1)] > img[(size_t)(r - 4) * wv + (wv - 9)];
-        } else {
-            carry = 0;
-        }
-        unsigned hi = carry << 31, lo = 0;
+    const int r = r0 + threadIdx.y, ca = c0 + kCenPx * threadIdx.x;
+    if (r >= hv || ca >= wv) return;
+    const int tr = threadIdx.y + kCenHaloV, tc = kCenPx * threadIdx.x + kCenOrg;
+    const bool row_ok = r >= 3 && r <= hv - 4;
+    // 9-bit groups per pixel, raster order: up[0..2] = rows r-3, r-2, r-1, mid = row r, dn[0..2] = rows r+1, r+2, r+3
+    unsigned up[kCenPx][3], dn[kCenPx][3], mid[kCenPx];
+    constexpr int NC = 9 + kCenPx - 1; // window columns ca-4 .. ca+4+(kCenPx-1)
 #pragma unroll
-        for (int y = -3; y <= 3; y++) {
+    for (int g = 0; g < 3; g++) {
+        int A[NC], B[NC]; // rows r-3+g and r+3-g
 #pragma unroll
-            for (int x = -4; x <= 4; x++) {
-                const int k = (y + 3) * 9 + (x + 4); // 0..62, bit position 62 - k
-                unsigned bit = T[tr + y][tc + x] > T[tr - y][tc - x];
-                if (k < 31) hi |= bit << (30 - k);
-                else lo |= bit << (62 - k);
+        for (int x = 0; x < NC; x++) { A[x] = T[tr - 3 + g][tc - 4 + x]; B[x] = T[tr + 3 - g][tc - 4 + x]; }
+#pragma unroll
+        for (int p = 0; p < kCenPx; p++) {
+            unsigned u = 0, l = 0;
+#pragma unroll
+            for (int x = 0; x < 9; x++) {
+                // offset (y, x-4) with y = g-3 < 0: X(r+y, c+x-4) > X(r-y, c-x+4);   offset (-y, x-4): the mirrored pair
+                u = __funnelshift_l((unsigned)(B[p + 8 - x] - A[p + x]), u, 1);
+                l = __funnelshift_l((unsigned)(A[p + 8 - x] - B[p + x]), l, 1);
             }
+            up[p][g] = u; dn[p][2 - g] = l;
         }
-        code = ((unsigned long long)hi << 32) | lo;
     }
-    out[(size_t)r * wv + c] = code;
+    {
+        int A[NC];
+#pragma unroll
+        for (int x = 0; x < NC; x++) A[x] = T[tr][tc - 4 + x];
+#pragma unroll
+        for (int p = 0; p < kCenPx; p++) {
+            unsigned m = 0;
+#pragma unroll
+            for (int x = 0; x < 9; x++) m = __funnelshift_l((unsigned)(A[p + 8 - x] - A[p + x]), m, 1);
+            mid[p] = m;
+        }
+    }
+    unsigned prev_last = 0; // bit 0 of the code of the pixel to the left, when that pixel has one
+    bool prev_valid = false;
+#pragma unroll
+    for (int p = 0; p < kCenPx; p++) {
+        const int c = ca + p;
+        if (c >= wv) break;
+        unsigned long long code = 0;
+        const bool valid = row_ok && c >= 4 && c <= wv - 5;
+        if (valid) {
+            // bit 63: the accumulator is not reset between pixels (census.cpp:30-51), it still holds the last bit of the
+            // pixel scanned before
+            unsigned carry;
+            if (prev_valid) {
+                carry = prev_last;
+            } else if (c > 4) {
+                carry = T[tr + 3][tc + p + 3] > T[tr - 3][tc + p - 5]; // previous pixel (r, c-1): X(r+3, c-1+4) > X(r-3, c-1-4)
+            } else if (r > 3) {
+                // previous pixel in raster order is (r-1, wv-5): X(r+2, wv-1) > X(r-4, wv-9)
+                carry = img[(size_t)(r + 2) * wv + (wv - 1)] > img[(size_t)(r - 4) * wv + (wv - 9)];
+            } else {
+                carry = 0;
+            }
+            // bit positions: carry 63, up[0] 62..54, up[1] 53..45, up[2] 44..36, mid 35..27, dn[0] 26..18, dn[1] 17..9, dn[2] 8..0
+            const unsigned hi = (carry << 31) | (up[p][0] << 22) | (up[p][1] << 13) | (up[p][2] << 4) | (mid[p] >> 5);
+            const unsigned lo = (mid[p] << 27) | (dn[p][0] << 18) | (dn[p][1] << 9) | dn[p][2];
+            code = ((unsigned long long)hi << 32) | lo;
+            prev_last = lo & 1u;
+        }
+        prev_valid = valid;
+        out[(size_t)r * wv + c] = code;
+    }
 }
 
 void launch_census(const uint8_t *oriented, const Dims &d, unsigned long long *census, cudaStream_t st, LaunchCounter &lc)
