@@ -448,6 +448,73 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
     // codes whose indices cover every residue mod 16 twice (once per half warp): conflict-free like the natural order.
     const int dl = d.interleaved ? 2 * d.nr * (lane >> 2) + (lane & 1) + d.nr * ((lane >> 1) & 1) : lane;
     auto dku = [&](int k) { return d.interleaved ? 2 * d.nr * ((8 * k) & (d.lpc - 1)) + 2 * ((8 * k) >> d.lpc_shift) : 32 * k; };
+    // Interior tiles (all but a frame of width ~D): every cell of every active view is a plain popcount, so the row loop
+    // needs no geometry at all -- one running shared-memory pointer per view (+-1 code per pixel for the horizontal views,
+    // one staged line per pixel for the vertical ones), a zero cell leaves as 16-byte stores, the 8-bit range is checked
+    // once per pixel. 244 -> ~95 instructions per pixel and warp; the popcounts (XU pipe) are then what is left.
+    if constexpr (NK > 0) {
+        auto plain_at = [&](int v, int ii, int jj) {
+            int rv, cc;
+            image_to_view(d, v, ii, jj, rv, cc);
+            return rv >= 3 && rv < view_rows(d, v) - 2 && cc >= D - 1;
+        };
+        bool interior = i0 + T <= d.Hp && j0 + T <= d.Wp;
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+            if ((any >> v) & 1u)
+                interior = interior && plain_at(v, i0, j0) && plain_at(v, i0, j0 + T - 1) && plain_at(v, i0 + T - 1, j0) && plain_at(v, i0 + T - 1, j0 + T - 1);
+        if (interior) { // block-uniform
+            const unsigned s_base = (unsigned)__cvta_generic_to_shared(s), c1_base = (unsigned)__cvta_generic_to_shared(sc1);
+            // code index of the d = 0 partner of pixel (li, lj = 0) in view v's staged lines, minus the lane's disparity part
+            unsigned pv[4];
+            pv[0] = s_base + 8u * (unsigned)((0 * T + li) * P + (D - 1) - dl);
+            pv[1] = s_base + 8u * (unsigned)((1 * T + li) * P + (T - 1) + (D - 1) - dl);
+            pv[2] = s_base + 8u * (unsigned)((2 * T + 0) * P + (T - 1 - li) + (D - 1) - dl);
+            pv[3] = s_base + 8u * (unsigned)((3 * T + 0) * P + li + (D - 1) - dl);
+            const int pstep[4] = {8, -8, 8 * P, 8 * P};
+            unsigned koff[NKC];
+#pragma unroll
+            for (int k = 0; k < NKC; k++) koff[k] = 8u * (unsigned)dku(k);
+            unsigned c1a = c1_base + 8u * (unsigned)(li * T); // + 8 * (v * T * T + lj)
+            uint8_t *dst = fused + ((size_t)i * d.Wp + j0) * D;
+#pragma unroll 1
+            for (int lj = 0; lj < T; lj++, dst += D, c1a += 8u) {
+                const unsigned m = smask[li * T + lj];
+                if (m == 0) { // warp-uniform; D is a multiple of 32 here: the cell is D / 16 aligned 16-byte stores
+                    if (lane < D / 16) *reinterpret_cast<uint4 *>(dst + 16 * lane) = make_uint4(0u, 0u, 0u, 0u);
+                    if (NK > 2 && lane + 32 < D / 16) *reinterpret_cast<uint4 *>(dst + 16 * (lane + 32)) = make_uint4(0u, 0u, 0u, 0u);
+                } else {
+                    unsigned acc[NKC];
+#pragma unroll
+                    for (int k = 0; k < NKC; k++) acc[k] = 0;
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        if (!((m >> v) & 1u)) continue; // warp-uniform
+                        const uint2 c1 = lds64(c1a + 8u * (unsigned)(v * T * T));
+#pragma unroll
+                        for (int k = 0; k < NKC; k++) {
+                            const uint2 x = lds64(pv[v] - koff[k]);
+                            acc[k] += __popc(x.x ^ c1.x) + __popc(x.y ^ c1.y);
+                        }
+                    }
+                    unsigned all = acc[0];
+#pragma unroll
+                    for (int k = 1; k < NKC; k++) all |= acc[k];
+                    if (all > 255u) { // cannot happen; kept as the literal formula's saturation + flag
+                        overflow = true;
+#pragma unroll
+                        for (int k = 0; k < NKC; k++) acc[k] = min(acc[k], 255u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < NKC; k++) dst[lane + 32 * k] = (uint8_t)acc[k];
+                }
+#pragma unroll
+                for (int v = 0; v < 4; v++) pv[v] += (unsigned)pstep[v];
+            }
+            if (overflow) atomicOr(status, kStatusFusedOverflow);
+            return;
+        }
+    }
 #pragma unroll 1
     for (int lj = 0; lj < T; lj++) {
         const int j = j0 + lj;
