@@ -36,6 +36,11 @@ __device__ __forceinline__ void red_min_shared_if(unsigned addr, unsigned val, b
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.min.u32 [%0], %1;\n\t}\n" ::"r"(addr), "r"(val), "r"((unsigned)pred) : "memory");
 }
+// 8-byte asynchronous global -> shared copy; nothing is read and zeros are written when !valid
+__device__ __forceinline__ void cp_async8_zfill(unsigned dst_s, const void *src, bool valid)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst_s), "l"(src), "r"(valid ? 8 : 0) : "memory");
+}
 __device__ __forceinline__ uint2 lds64(unsigned addr)
 {
     uint2 v;
@@ -375,7 +380,9 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
 // the view column is >= D - 1, so every d has a partner and the cost is a plain popcount. Anything else takes the
 // literal per-cell formula of census.cpp:63-88,95-98 / hpp:264-276 below.
 // grid (ceil(Wp/T), ceil(Hp/T)), block 32 * T, dynamic smem 4 * T * (T + D) u64 + 4 * T * T u64 + T * T bytes
-template <int T, int NK> // NK = D / 32 when D is a multiple of 32 (fully unrolled), 0 = any D
+// ORDER: 0 = the cell's byte order is read from Dims at run time; 1 = natural; 2 = lane-interleaved with lpc 16 and
+// nr = NK (D = 32 * nr: the per-k disparity offsets are then compile-time constants and fold into the load addresses)
+template <int T, int NK, int ORDER> // NK = D / 32 when D is a multiple of 32 (fully unrolled), 0 = any D
 __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__restrict__ census, const uint8_t *__restrict__ masks,
                                                  Dims d, unsigned view_mask, uint8_t *__restrict__ fused, int *__restrict__ status, int row_lo)
 {
@@ -420,9 +427,12 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
         const bool row_ok = rv >= 0 && rv < hv;
         const unsigned long long *src = c2 + (size_t)(row_ok ? rv : 0) * wv;
         const int col0 = cv_lo[v] - (D - 1);
+        // asynchronous copies (zero-filled outside the view): the 4 x 7 loads of a thread are all in flight at once instead of
+        // each waiting for its shared-memory store
         for (int x = tid & 31; x < P - 1; x += 32) {
             const int col = col0 + x;
-            sv[line * P + x] = (row_ok && col >= 0 && col < wv) ? __ldg(src + col) : 0ull;
+            const bool in = row_ok && col >= 0 && col < wv;
+            cp_async8_zfill((unsigned)__cvta_generic_to_shared(sv + line * P + x), src + (in ? col : 0), in);
         }
         // the centre codes of the tile's pixels (row `line` of the tile)
         if ((tid & 31) < T) {
@@ -436,6 +446,7 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
             sc1[(v * T + line) * T + (tid & 31)] = c;
         }
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
     const int lane = tid & 31, li = tid >> 5;
     const int i = i0 + li;
@@ -447,7 +458,11 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
     // straddles a row of the word matrix): d = dl + dku(k). Within a k the 32 lanes still read 32 distinct 8-byte census
     // codes whose indices cover every residue mod 16 twice (once per half warp): conflict-free like the natural order.
     const int dl = d.interleaved ? 2 * d.nr * (lane >> 2) + (lane & 1) + d.nr * ((lane >> 1) & 1) : lane;
-    auto dku = [&](int k) { return d.interleaved ? 2 * d.nr * ((8 * k) & (d.lpc - 1)) + 2 * ((8 * k) >> d.lpc_shift) : 32 * k; };
+    auto dku = [&](int k) {
+        if constexpr (ORDER == 1) return 32 * k;
+        else if constexpr (ORDER == 2) return 2 * NK * ((8 * k) & 15) + 2 * ((8 * k) >> 4);
+        else return d.interleaved ? 2 * d.nr * ((8 * k) & (d.lpc - 1)) + 2 * ((8 * k) >> d.lpc_shift) : 32 * k;
+    };
     // Interior tiles (all but a frame of width ~D): every cell of every active view is a plain popcount, so the row loop
     // needs no geometry at all -- one running shared-memory pointer per view (+-1 code per pixel for the horizontal views,
     // one staged line per pixel for the vertical ones), a zero cell leaves as 16-byte stores, the 8-bit range is checked
@@ -573,18 +588,27 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
     if (overflow) atomicOr(status, kStatusFusedOverflow);
 }
 
-template <int T, int NK>
-static void launch_fuse_t(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
+template <int T, int NK, int ORDER>
+static void launch_fuse_o(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
                           int *status, cudaStream_t st, int row_lo, int row_hi)
 {
     const size_t smem = (size_t)4 * T * (T + d.D) * 8 + (size_t)4 * T * T * 8 + T * T;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_fuse<T, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_fuse<T, NK, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_done = true;
     }
     dim3 grid((d.Wp + T - 1) / T, (row_hi - row_lo + T - 1) / T);
-    k_fuse<T, NK><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, status, row_lo);
+    k_fuse<T, NK, ORDER><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, status, row_lo);
+}
+
+template <int T, int NK>
+static void launch_fuse_t(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
+                          int *status, cudaStream_t st, int row_lo, int row_hi)
+{
+    if (NK > 0 && d.interleaved && d.lpc == 16 && d.nr == NK) launch_fuse_o<T, NK, (NK > 0 ? 2 : 0)>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi);
+    else if (NK > 0 && !d.interleaved) launch_fuse_o<T, NK, (NK > 0 ? 1 : 0)>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi);
+    else launch_fuse_o<T, NK, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi);
 }
 
 void launch_fuse(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
