@@ -16,7 +16,7 @@ def engine():
     import sister_b200
     if not os.path.exists(sister_b200.library_path()):
         sister_b200.build_library()
-    eng = sister_b200.Engine(256, 256, 64, n_slots=3)
+    eng = sister_b200.Engine(256, 256, 96, n_slots=3)
     eng.set_test_taps(True)
     yield eng
     eng.close()
@@ -38,7 +38,8 @@ def test_golden_rigs(engine, name):
     assert outs2[0] is None and (outs2[1] == g["disp_h"]).all() and (outs2[2] == g["disp_v"]).all()
 
 
-@pytest.mark.parametrize("w,h,D,kind,seed", [(96, 64, 32, "smooth", 11), (40, 56, 8, "plane", 12), (72, 60, 24, "smooth", 13)])
+@pytest.mark.parametrize("w,h,D,kind,seed", [(96, 64, 32, "smooth", 11), (40, 56, 8, "plane", 12), (72, 60, 24, "smooth", 13),
+                                                 (48, 40, 96, "smooth", 14)])  # D = 32, 96: lane-interleaved cells (4 chains per warp)
 def test_every_stage_against_oracle(engine, oracle_lib, w, h, D, kind, seed):
     views = make_rig(w, h, D, seed=seed, kind=kind, channels=3)
     wp, hp = w + 2 * D, h + 2 * D
@@ -190,7 +191,8 @@ def test_full_size_properties():
             assert (r[0] == a[0]).all()
 
 
-@pytest.mark.parametrize("w,h,D,seed,modes", [(64, 48, 384, 21, 1), (32, 16, 512, 22, 1), (40, 32, 264, 23, 7)])
+@pytest.mark.parametrize("w,h,D,seed,modes", [(64, 48, 384, 21, 1), (32, 16, 512, 22, 1), (40, 32, 264, 23, 7),
+                                                  (48, 32, 320, 24, 1)])  # D = 320: lane-interleaved cells, 10 registers per lane
 def test_large_disparity_ranges_against_oracle(oracle_lib, w, h, D, seed, modes):
     """D beyond the reference's own limit (postprocess.cpp:193 overflows at D >= 272): the widened oracle is the check
     (BASELINE.json configs[3]/[4] use D = 384 and 512)."""
