@@ -140,7 +140,7 @@ def run_reference(args):
                          "sample": "1 rig per step, one doMultiStereo(mode 0) on the padded frame (hpp:152-295) via the L2 functions"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -171,7 +171,27 @@ def cpu_baseline_leg(budget_s: float = 25.0):
             "gcost_evals_per_s": n / dt * cost_evals(W_, H_, D_) / 1e9}
 
 
+# The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner to fd 1 under
+# torchrun), so fd 1 is pointed at stderr for the whole run and the line goes to the original stdout.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
@@ -336,7 +356,7 @@ def main():
         except Exception as ex:  # the baseline is informative; never lose the GPU line to it
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
