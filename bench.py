@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rigs-per-step", type=int, default=8, help="rigs per GPU per step")
+    ap.add_argument("--rigs-per-step", type=int, default=16, help="rigs per GPU per step (the end-to-end call drains its pipeline once per step: 8 rigs lose 3 %, 16 lose 1.5 %)")
     ap.add_argument("--slots", type=int, default=4, help="rigs in flight per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

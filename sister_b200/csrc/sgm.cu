@@ -26,11 +26,20 @@
 //     output encoding (hpp:111-118) in the same sweep; S itself is only written when a test asks for it.
 //
 // Traffic per padded cell: 8 x (1 B read C + 1 B write Q) + (1 + 8) B read = 25 B, no read-modify-write, against
-// 40 B for the path-by-path accumulation into a uint16 sum volume this replaces. The fused-cost cells a chain will
-// need are known in advance, so each lane loads its bytes kAhead steps early into registers and asks L2 for the cell
-// kFar steps beyond that. On B200 the path kernel is bound by DRAM (about 5 TB/s of mixed reads and writes in
-// scattered runs of 192-byte cells), not by issue slots: halving the instruction count, doubling the warps or
-// deepening the prefetch each moved it by less than 5 % (profiles/r01_ncu_v16_paths.txt).
+// 40 B for the path-by-path accumulation into a uint16 sum volume this replaces (crop only: 14 B per padded cell).
+//
+// How the path kernel runs (with the measurements behind each choice):
+//   * cells are stored in the CELL ORDER of common.cuh (lane-interleaved words when the chain's lanes are exactly full), so
+//     a chain's load / store instruction covers 4 * lpc contiguous bytes and bytes <-> packed registers is two
+//     instructions per word;
+//   * full-lane chains stage the cost stream through a per-warp cp.async ring in shared memory (run_chain_ring: lookahead
+//     of kRing - 1 steps, no lookahead registers), the other sizes keep the register lookahead of run_chain;
+//   * between border crossings, away from the chain's end and on one side of a region edge the step loop runs a body
+//     without wrap tests, guards or border selects ("fast phases");
+//   * warps are handed out from an interleaved table (warp_order_for) so that every SM gets the same mix of sections.
+// The kernel is bound by issue slots while all its blocks are resident and by the step's dependent latency in the thinly
+// occupied second wave (5568 warps on 148 x 24 slots at config 2); it is not bound by DRAM (no stores: -0.12 ms, no
+// loads: -0.09 ms of 0.74 ms).
 #include <algorithm>
 #include <cstdlib>
 #include <initializer_list>
