@@ -195,24 +195,31 @@ __device__ __forceinline__ int median9(int v0, int v1, int v2, int v3, int v4, i
     return v4;
 }
 
-// packed s16x2 compare-exchange: two pixels per register
-__device__ __forceinline__ void sort2p(uint32_t &a, uint32_t &b)
+// Median of nine on two pixels at once (packed s16x2). The value of a median does not depend on the network that finds
+// it, so instead of the 19 compare-exchanges of postprocess.cpp:52-58 (38 min / max): sort the three columns, then
+// med3(max of the minima, med3 of the middles, min of the maxima). With three-input packed min / max (VIMNMX3) and the
+// middle of three as a ^ b ^ c ^ min ^ max (the three outputs are a permutation of the three inputs) that is 22
+// instructions, and the kernel is bound by exactly these.
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
+__device__ __forceinline__ void sort3p(uint32_t a, uint32_t b, uint32_t c, uint32_t &lo, uint32_t &mid, uint32_t &hi)
 {
-    const uint32_t lo = __vmins2(a, b), hi = __vmaxs2(a, b);
-    a = lo; b = hi;
+    lo = __vimin3_s16x2(a, b, c);
+    hi = __vimax3_s16x2(a, b, c);
+    mid = xor3(xor3(a, b, c), lo, hi);
 }
-// the 19-exchange network of postprocess.cpp:52-58 on two pixels at once
+__device__ __forceinline__ uint32_t med3p(uint32_t a, uint32_t b, uint32_t c)
+{
+    return xor3(xor3(a, b, c), __vimin3_s16x2(a, b, c), __vimax3_s16x2(a, b, c));
+}
+// v0 v1 v2 / v3 v4 v5 / v6 v7 v8: rows of the 3 x 3 window; columns are (v0, v3, v6), (v1, v4, v7), (v2, v5, v8)
 __device__ __forceinline__ uint32_t median9p(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t v4, uint32_t v5, uint32_t v6,
                                              uint32_t v7, uint32_t v8)
 {
-    sort2p(v1, v2); sort2p(v4, v5); sort2p(v7, v8);
-    sort2p(v0, v1); sort2p(v3, v4); sort2p(v6, v7);
-    sort2p(v1, v2); sort2p(v4, v5); sort2p(v7, v8);
-    sort2p(v0, v3); sort2p(v5, v8); sort2p(v4, v7);
-    sort2p(v3, v6); sort2p(v1, v4); sort2p(v2, v5);
-    sort2p(v4, v7); sort2p(v4, v2); sort2p(v6, v4);
-    sort2p(v4, v2);
-    return v4;
+    uint32_t l0, m0, h0, l1, m1, h1, l2, m2, h2;
+    sort3p(v0, v3, v6, l0, m0, h0);
+    sort3p(v1, v4, v7, l1, m1, h1);
+    sort3p(v2, v5, v8, l2, m2, h2);
+    return med3p(__vimax3_s16x2(l0, l1, l2), med3p(m0, m1, m2), __vimin3_s16x2(h0, h1, h2));
 }
 
 // One block per map (8 maps: L and R of 4 views). Flat-array recursion (see oracle/sister_oracle.c
