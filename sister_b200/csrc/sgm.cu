@@ -427,7 +427,8 @@ __device__ __forceinline__ void run_chain_ring(const uint8_t *__restrict__ fused
     constexpr int NCP = (NCH + 31) / 32;
     constexpr int SS = (32 / LPC) * D; // bytes per ring slot
     constexpr int R = kRing, A = R - 1;
-    constexpr int U = 2;               // steps per trip of the main loops
+    constexpr int U = R / 2;           // steps per trip of the main loops: half a ring, so that slot offsets are immediates
+    static_assert(R == 2 * U, "a trip of the step loops walks half of the ring");
     // copy cursors: chunk g = lane + 32 n of the warp step belongs to the cell of chain g / CH
     Cursor cp[NCP];
     const uint8_t *cp_src[NCP];
@@ -466,7 +467,9 @@ __device__ __forceinline__ void run_chain_ring(const uint8_t *__restrict__ fused
 #pragma unroll
     for (int t = 0; t < A; t++) copy_step(t, t * SS);
     const unsigned rd_lane = ring_s + (lane / LPC) * D + li.template cell_offset<IL>();
-    unsigned rd_off = 0, wr_off = A * SS; // slot of the current step / of the step A ahead (the one consumed last)
+    // Step u of a trip reads slot half / SS + u and refills the slot consumed one step earlier with the step A ahead; the
+    // trips alternate between the ring's two halves (half <-> other), so inside a trip every slot offset is an immediate.
+    unsigned half = 0, other = U * SS;
     Cursor st = first;
     ChainState<NR> cs;
     uint32_t mm = 0;          // KIND 1: minimum of the truncated state
@@ -479,11 +482,11 @@ __device__ __forceinline__ void run_chain_ring(const uint8_t *__restrict__ fused
         chain_resume<NR, LPC, true>(cs, a, li);
     }
     // the slot of the current step has landed (every lane waits for its own copies, then the warp meets); read it
-    auto fetch = [&](uint32_t (&c)[NR], const bool zero_invalid) {
+    auto fetch = [&](const int u, uint32_t (&c)[NR], const bool zero_invalid) {
         cp_async_wait<A - 1>();
         __syncwarp();
         uint32_t w[NR / 2];
-        ring_read<NR, LPC, IL>(rd_lane + rd_off, w);
+        ring_read<NR, LPC, IL>(rd_lane + half + u * SS, w);
         // the first line of a pass reads an invalid cost (255, census.cpp:76) as 0 (sgm.cpp:109,123,146); fused volumes
         // never hold 255 (match.cu), the raw two-view volume of sister_stereo does
         if (zero_invalid) {
@@ -492,15 +495,12 @@ __device__ __forceinline__ void run_chain_ring(const uint8_t *__restrict__ fused
         }
         unpack_cost<NR, IL>(w, c);
     };
-    auto turn = [&]() {
-        wr_off = rd_off;
-        rd_off = rd_off + SS == R * SS ? 0u : rd_off + SS;
-    };
-    auto step = [&](const int s) {
+    auto wr_off = [&](const int u) { return u == 0 ? other + (U - 1) * SS : half + (u - 1) * SS; };
+    auto next_trip = [&]() { const unsigned t = half; half = other; other = t; };
+    auto step = [&](const int s, const int u) {
         uint32_t c[NR], q[NR];
-        fetch(c, KIND == 1 || (KIND == 2 && starts_on_first_line && s == 0));
-        copy_step(s + A, wr_off);
-        turn();
+        fetch(u, c, KIND == 1 || (KIND == 2 && starts_on_first_line && s == 0));
+        copy_step(s + A, wr_off(u));
         uint8_t *dst = q_lane + (long long)st.off8 * 8;
         const bool wanted = in_roi<DIAG>(st, wk);
         const bool off_next = advance<DIAG>(st, wk); // KIND 2: the next cell follows a border crossing
@@ -526,17 +526,17 @@ __device__ __forceinline__ void run_chain_ring(const uint8_t *__restrict__ fused
         w_lo = wk.sj > 0 ? wk.c0 - first.j : first.j - (wk.c0 + (int)wk.nc - 1);
         w_hi = wk.sj > 0 ? wk.c0 + (int)wk.nc - first.j : first.j - wk.c0 + 1;
     }
-    auto fast_step = [&](auto store_tag) {
+    const uint8_t *cp_ptr[NCP]; // fast runs: the copy cursors as running pointers
+    auto fast_step = [&](const int u, auto store_tag) {
         constexpr bool STORE = decltype(store_tag)::value;
         uint32_t c[NR], q[NR];
-        fetch(c, false);
+        fetch(u, c, false);
 #pragma unroll
         for (int n = 0; n < NCP; n++) {
-            if (cp_on[n]) cp_async16(cp_dst[n] + wr_off, cp_src[n] + (long long)cp[n].off8 * 8);
-            cp[n].off8 += cp_stride8[n];
+            if (cp_on[n]) cp_async16(cp_dst[n] + wr_off(u), cp_ptr[n]);
+            cp_ptr[n] += (long long)cp_stride8[n] * 8;
         }
         cp_async_commit();
-        turn();
         chain_step<NR, LPC, true>(cs, c, li, q);
         if constexpr (STORE) {
             uint8_t *dst = q_lane + (long long)st.off8 * 8;
@@ -567,32 +567,42 @@ __device__ __forceinline__ void run_chain_ring(const uint8_t *__restrict__ fused
             nfast = (room >= 2 * U && s0 > 0) ? room / U : 0; // trips of U steps; step 0 is special (first line)
         }
         if (nfast > 0) {
+#pragma unroll
+            for (int n = 0; n < NCP; n++) cp_ptr[n] = cp_src[n] + (long long)cp[n].off8 * 8;
             if (inside) {
 #pragma unroll 1
                 for (int g = 0; g < nfast; g++) {
 #pragma unroll
-                    for (int u = 0; u < U; u++) fast_step(std::true_type{});
+                    for (int u = 0; u < U; u++) fast_step(u, std::true_type{});
+                    next_trip();
                 }
                 if constexpr (!DIAG) st.j += nfast * U * wk.sj;
             } else {
 #pragma unroll 1
                 for (int g = 0; g < nfast; g++) {
 #pragma unroll
-                    for (int u = 0; u < U; u++) fast_step(std::false_type{});
+                    for (int u = 0; u < U; u++) fast_step(u, std::false_type{});
+                    next_trip();
                 }
                 st.j += nfast * U * wk.sj;
             }
             st.i += nfast * U * wk.si;
 #pragma unroll
-            for (int n = 0; n < NCP; n++) { cp[n].j += nfast * U * wk.sj; cp[n].i += nfast * U * wk.si; }
+            for (int n = 0; n < NCP; n++) {
+                cp[n].off8 += nfast * U * cp_stride8[n];
+                cp[n].j += nfast * U * wk.sj; cp[n].i += nfast * U * wk.si;
+            }
             s0 += nfast * U;
         } else {
 #pragma unroll
-            for (int u = 0; u < U; u++) step(s0 + u);
+            for (int u = 0; u < U; u++) step(s0 + u, u);
+            next_trip();
             s0 += U;
         }
     }
-    if (s0 < nsteps) step(s0); // warp-uniform
+#pragma unroll
+    for (int u = 0; u < U - 1; u++)
+        if (s0 + u < nsteps) step(s0 + u, u); // warp-uniform
     cp_async_wait<0>();
     if (KIND == 2 && state_out) store_q<NR, LPC, true, IL>(state_out, cs.a, 2 * NR); // a <= P2 fits a byte
 }
