@@ -234,6 +234,7 @@ __device__ __forceinline__ uint32_t median9p(uint32_t v0, uint32_t v1, uint32_t 
 //   * one thread does the first pair and then the last pair of the row (which needs the row's first output).
 // grid 8, block 1024, dynamic smem (kMedRing + 4) * wv int16
 constexpr int kMedRing = 8, kMedAhead = 6;
+constexpr int kMedInterior = 24 * 32; // threads of the warps with (warp & 3) != 3 in a block of 1024
 
 __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wtaL, const int16_t *__restrict__ wtaR, Dims d,
                                                  unsigned view_mask, int16_t *__restrict__ medL, int16_t *__restrict__ medR)
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wta
     const int RS = kMedRing * wv, FS = 4 * wv;
     const long long N = (long long)hv * wv;
     const long long p_lo = wv + 1, p_hi = N - wv - 5;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
     const int chunks = wv >> 2; // 8-byte chunks per row (wv % 4 == 0, postprocess.cpp:18)
     auto stage = [&](int row) {
         if (row < hv) {
@@ -279,6 +280,34 @@ __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wta
         const int rb1 = ((r + 1) % kMedRing) * wv;                  // raw ring index of (r+1, 0)
         const bool plain_row = r >= 2 && r <= hv - 3;               // no position of this row is special
         // ---- interior pairs (c, c+1), c even in [2, wv-4]: all nine neighbours lie inside the rows' own slots ----
+        // Plain rows (all but the first and the last two): the warps of three of the SM's four schedulers take two adjacent
+        // pairs per thread -- 8-byte loads, and the sorted column between the two pairs is shared -- and leave the fourth
+        // scheduler to the border warp below, whose dependent chain (column w-1 waits for column 0) is the row's critical
+        // path and otherwise gets one issue slot in eight.
+        if (plain_row) {
+            if ((warp & 3) != 3) {
+                const int hmax = (wv - 4) >> 1; // pairs 1 .. hmax
+                const uint2 *fp2 = reinterpret_cast<const uint2 *>(filt32 + (fprev >> 1));
+                const uint2 *rq2 = reinterpret_cast<const uint2 *>(ring32 + (rb >> 1));
+                const uint2 *rs2 = reinterpret_cast<const uint2 *>(ring32 + (rb1 >> 1));
+                uint32_t *fcw = reinterpret_cast<uint32_t *>(filt) + (fcur >> 1);
+                uint32_t *orow = reinterpret_cast<uint32_t *>(out + base);
+                for (int t = (warp - (warp >> 2)) * 32 + lane; 1 + 2 * t <= hmax; t += kMedInterior) {
+                    // words 2t .. 2t+3 of the three window rows: pairs h0 = 2t+1 (a b c) and h1 = 2t+2 (b c d)
+                    const uint2 p0 = fp2[t], p1 = fp2[t + 1], q0 = rq2[t], q1 = rq2[t + 1], s0 = rs2[t], s1 = rs2[t + 1];
+                    uint32_t l[5], m[5], h[5];
+                    sort3p(__byte_perm(p0.x, p0.y, 0x5432), __byte_perm(q0.x, q0.y, 0x5432), __byte_perm(s0.x, s0.y, 0x5432), l[0], m[0], h[0]);
+                    sort3p(p0.y, q0.y, s0.y, l[1], m[1], h[1]);
+                    sort3p(__byte_perm(p0.y, p1.x, 0x5432), __byte_perm(q0.y, q1.x, 0x5432), __byte_perm(s0.y, s1.x, 0x5432), l[2], m[2], h[2]);
+                    sort3p(p1.x, q1.x, s1.x, l[3], m[3], h[3]);
+                    sort3p(__byte_perm(p1.x, p1.y, 0x5432), __byte_perm(q1.x, q1.y, 0x5432), __byte_perm(s1.x, s1.y, 0x5432), l[4], m[4], h[4]);
+                    const uint32_t v0 = med3p(__vimax3_s16x2(l[0], l[1], l[2]), med3p(m[0], m[1], m[2]), __vimin3_s16x2(h[0], h[1], h[2]));
+                    const uint32_t v1 = med3p(__vimax3_s16x2(l[2], l[3], l[4]), med3p(m[2], m[3], m[4]), __vimin3_s16x2(h[2], h[3], h[4]));
+                    fcw[2 * t + 1] = v0; orow[2 * t + 1] = v0;
+                    if (2 * t + 2 <= hmax) { fcw[2 * t + 2] = v1; orow[2 * t + 2] = v1; }
+                }
+            }
+        } else
         for (int c = 2 + 2 * tid; c <= wv - 4; c += 2 * nt) {
             const int h = c >> 1;
             const uint32_t pa = filt32[(fprev >> 1) + h - 1], pb = filt32[(fprev >> 1) + h], pc = filt32[(fprev >> 1) + h + 1];
@@ -303,8 +332,7 @@ __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wta
         // nine with one unknown x is clamp(x, k3, k4) with k3, k4 the 4th and 5th smallest of the other eight, and
         // those are the network's outputs for x = -inf and x = +inf -- evaluated together as the two packed halves, in
         // parallel with column 0, so the row's critical path is one network, not two. ----
-        if (tid >= nt - 32) {
-            const int lane = tid & 31;
+        if (warp == 3) {
             auto F = [&](int idx) -> int { if (idx < 0) idx += FS; if (idx >= FS) idx -= FS; return filt[idx]; };
             auto R = [&](int idx) -> int { if (idx < 0) idx += RS; if (idx >= RS) idx -= RS; return ring[idx]; };
             auto dup = [](int x) -> uint32_t { return ((uint32_t)x & 0xFFFFu) * 0x10001u; };
