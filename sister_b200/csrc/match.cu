@@ -232,9 +232,10 @@ __device__ __forceinline__ uint32_t median9p(uint32_t v0, uint32_t v1, uint32_t 
 //     the filtered rows through a flat ring of 4 rows, so that "previous element of column 0" and "next element of
 //     column w-1" are plain flat neighbours, exactly as in the reference's flat pointer walk;
 //   * one thread does the first pair and then the last pair of the row (which needs the row's first output).
+//   * warps are given roles by scheduler: the border warp alone on one, the interior warps on the other three, and the
+//     warps without a role leave at once (the barrier counts the ones that stay).
 // grid 8, block 1024, dynamic smem (kMedRing + 4) * wv int16
 constexpr int kMedRing = 8, kMedAhead = 6;
-constexpr int kMedInterior = 24 * 32; // threads of the warps with (warp & 3) != 3 in a block of 1024
 
 __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wtaL, const int16_t *__restrict__ wtaR, Dims d,
                                                  unsigned view_mask, int16_t *__restrict__ medL, int16_t *__restrict__ medR)
@@ -251,13 +252,27 @@ __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wta
     const int RS = kMedRing * wv, FS = 4 * wv;
     const long long N = (long long)hv * wv;
     const long long p_lo = wv + 1, p_hi = N - wv - 5;
-    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Roles by scheduler (a warp runs on scheduler warp & 3): warp 3 is the border warp and has scheduler 3 to itself -- the
+    // other warps of that scheduler leave at once, so that not even their loop bookkeeping competes with it -- and the 24
+    // warps of schedulers 0..2 are the interior threads, numbered ti = 0 .. nt-1.
+    // Only as many interior warps stay as the row has pairs of pairs (13 of 24 at 1664 columns): every warp that stays
+    // pays the row loop's bookkeeping on its scheduler.
+    if ((warp & 3) == 3 && warp != 3) return;
+    const bool interior = (warp & 3) != 3;
+    const int iw = warp - (warp >> 2);                          // interior warp number 0..23
+    int n_iw = ((((wv - 4) >> 1) + 1) / 2 + 31) / 32;           // warps needed for two pairs per thread
+    n_iw = n_iw < 1 ? 1 : n_iw > 24 ? 24 : n_iw;
+    if (interior && iw >= n_iw) return;
+    const int ti = iw * 32 + lane, nt = n_iw * 32;
+    const int n_sync = nt + 32;                                 // the interior warps that stay + the border warp
+    auto block_sync = [&]() { asm volatile("bar.sync 1, %0;\n" ::"r"(n_sync) : "memory"); };
     const int chunks = wv >> 2; // 8-byte chunks per row (wv % 4 == 0, postprocess.cpp:18)
     auto stage = [&](int row) {
         if (row < hv) {
             const int16_t *src = raw + (size_t)row * wv;
             const unsigned dst = ring_s + 2u * (unsigned)((row % kMedRing) * wv);
-            for (int c = tid; c < chunks; c += nt)
+            for (int c = interior ? ti : chunks; c < chunks; c += nt)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + 8u * c), "l"(src + 4 * c) : "memory");
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -265,14 +280,14 @@ __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wta
     for (int row = 0; row < kMedAhead; row++) stage(row);
     // row 0 is copied unchanged
     asm volatile("cp.async.wait_group %0;\n" ::"n"(kMedAhead - 1) : "memory");
-    __syncthreads();
-    for (int c = tid; c < wv; c += nt) { const int16_t x = ring[c]; filt[c] = x; out[c] = x; }
+    block_sync();
+    for (int c = interior ? ti : wv; c < wv; c += nt) { const int16_t x = ring[c]; filt[c] = x; out[c] = x; }
     const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(ring);
     const uint32_t *filt32 = reinterpret_cast<const uint32_t *>(filt);
     for (int r = 1; r < hv; r++) {
         // rows <= r + 2 must have landed: rows 0 .. kMedAhead + r - 2 are committed
         asm volatile("cp.async.wait_group %0;\n" ::"n"(kMedAhead - 4) : "memory");
-        __syncthreads(); // publishes the raw rows and the filtered row r - 1; everyone is done with row r - 1
+        block_sync(); // publishes the raw rows and the filtered row r - 1; everyone is done with row r - 1
         stage(kMedAhead + r - 1);
         const long long base = (long long)r * wv;
         const int fprev = ((r - 1) & 3) * wv, fcur = (r & 3) * wv; // flat ring index of column 0 of rows r-1, r
@@ -285,14 +300,14 @@ __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wta
         // scheduler to the border warp below, whose dependent chain (column w-1 waits for column 0) is the row's critical
         // path and otherwise gets one issue slot in eight.
         if (plain_row) {
-            if ((warp & 3) != 3) {
+            if (interior) {
                 const int hmax = (wv - 4) >> 1; // pairs 1 .. hmax
                 const uint2 *fp2 = reinterpret_cast<const uint2 *>(filt32 + (fprev >> 1));
                 const uint2 *rq2 = reinterpret_cast<const uint2 *>(ring32 + (rb >> 1));
                 const uint2 *rs2 = reinterpret_cast<const uint2 *>(ring32 + (rb1 >> 1));
                 uint32_t *fcw = reinterpret_cast<uint32_t *>(filt) + (fcur >> 1);
                 uint32_t *orow = reinterpret_cast<uint32_t *>(out + base);
-                for (int t = (warp - (warp >> 2)) * 32 + lane; 1 + 2 * t <= hmax; t += kMedInterior) {
+                for (int t = ti; 1 + 2 * t <= hmax; t += nt) {
                     // words 2t .. 2t+3 of the three window rows: pairs h0 = 2t+1 (a b c) and h1 = 2t+2 (b c d)
                     const uint2 p0 = fp2[t], p1 = fp2[t + 1], q0 = rq2[t], q1 = rq2[t + 1], s0 = rs2[t], s1 = rs2[t + 1];
                     uint32_t l[5], m[5], h[5];
@@ -308,7 +323,7 @@ __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wta
                 }
             }
         } else
-        for (int c = 2 + 2 * tid; c <= wv - 4; c += 2 * nt) {
+        for (int c = interior ? 2 + 2 * ti : wv; c <= wv - 4; c += 2 * nt) {
             const int h = c >> 1;
             const uint32_t pa = filt32[(fprev >> 1) + h - 1], pb = filt32[(fprev >> 1) + h], pc = filt32[(fprev >> 1) + h + 1];
             const uint32_t qa = ring32[(rb >> 1) + h - 1], qb = ring32[(rb >> 1) + h], qc = ring32[(rb >> 1) + h + 1];
