@@ -550,16 +550,32 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
                     if (NK > 2 && lane + 32 < D / 16) *reinterpret_cast<uint4 *>(dst + 16 * (lane + 32)) = make_uint4(0u, 0u, 0u, 0u);
                 } else {
                     unsigned acc[NKC];
+                    if (m == 0xFu) { // all four views (the common case of mode 0): straight-line, no per-view branches
+                        uint2 c1[4];
 #pragma unroll
-                    for (int k = 0; k < NKC; k++) acc[k] = 0;
-#pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        if (!((m >> v) & 1u)) continue; // warp-uniform
-                        const uint2 c1 = lds64(c1a + 8u * (unsigned)(v * T * T));
+                        for (int v = 0; v < 4; v++) c1[v] = lds64(c1a + 8u * (unsigned)(v * T * T));
 #pragma unroll
                         for (int k = 0; k < NKC; k++) {
-                            const uint2 x = lds64(pv[v] - koff[k]);
-                            acc[k] += __popc(x.x ^ c1.x) + __popc(x.y ^ c1.y);
+                            unsigned a = 0;
+#pragma unroll
+                            for (int v = 0; v < 4; v++) {
+                                const uint2 x = lds64(pv[v] - koff[k]);
+                                a += __popc(x.x ^ c1[v].x) + __popc(x.y ^ c1[v].y);
+                            }
+                            acc[k] = a;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NKC; k++) acc[k] = 0;
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            if (!((m >> v) & 1u)) continue; // warp-uniform
+                            const uint2 c1 = lds64(c1a + 8u * (unsigned)(v * T * T));
+#pragma unroll
+                            for (int k = 0; k < NKC; k++) {
+                                const uint2 x = lds64(pv[v] - koff[k]);
+                                acc[k] += __popc(x.x ^ c1.x) + __popc(x.y ^ c1.y);
+                            }
                         }
                     }
                     unsigned all = acc[0];
