@@ -131,7 +131,7 @@ def run_reference(args):
     evals = cost_evals(W_, H_, D_)
     cores = 4 if ref is not None else 1  # census.cpp:117: 4 OpenMP sections in hammingCost, 1 thread elsewhere
     line = {
-        "impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": 0, "steps": args.steps,
+        "impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "gpus_used": 0, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u16", "data": "synthetic",
         "gcost_evals_per_s": fps * evals / 1e9,
