@@ -19,14 +19,17 @@ from sister_b200.synth import make_rig  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
-# (name, W, H, D, seed, kind)
+# (name, W, H, D, seed, kind, colour)
 RIGS = [
-    ("rig_64x48_d16", 64, 48, 16, 1234, "smooth"),
-    ("rig_40x56_d8", 40, 56, 8, 1235, "plane"),       # portrait
-    ("rig_96x64_d32", 96, 64, 32, 1236, "smooth"),
-    ("rig_160x120_d32", 160, 120, 32, 1237, "smooth"),
-    ("rig_128x96_d64", 128, 96, 64, 1238, "smooth"),
-    ("rig_72x60_d24", 72, 60, 24, 1239, "plane"),      # D not a multiple of 16/32
+    ("rig_64x48_d16", 64, 48, 16, 1234, "smooth", False),
+    ("rig_40x56_d8", 40, 56, 8, 1235, "plane", False),       # portrait
+    ("rig_96x64_d32", 96, 64, 32, 1236, "smooth", False),
+    ("rig_160x120_d32", 160, 120, 32, 1237, "smooth", False),
+    ("rig_128x96_d64", 128, 96, 64, 1238, "smooth", False),
+    ("rig_72x60_d24", 72, 60, 24, 1239, "plane", False),      # D not a multiple of 16/32
+    # true colour (B != G != R): the fixed-point BGR2GRAY of hpp:29-33 on what cv::imread hands over (compute_disp.cpp:19-23)
+    ("rig_96x64_d32_colour", 96, 64, 32, 1240, "smooth", True),
+    ("rig_80x72_d24_colour", 80, 72, 24, 1241, "smooth", True),
 ]
 
 
@@ -39,11 +42,11 @@ def main():
     ref = oracle.Ref()
     orc = oracle.Oracle()
     os.makedirs(OUT, exist_ok=True)
-    for name, w, h, D, seed, kind in RIGS:
-        views = make_rig(w, h, D, seed=seed, kind=kind, channels=3)
+    for name, w, h, D, seed, kind, colour in RIGS:
+        views = make_rig(w, h, D, seed=seed, kind=kind, channels=3, colour=colour)
         mv, hz, vt = ref.compute_disparities(views, D)
         pads = [orc.pad_replicate(orc.grey_bgr(v), D) for v in views]
-        rec = dict(w=w, h=h, D=D, seed=seed, kind=str(kind), disp_mv=mv, disp_h=hz, disp_v=vt,
+        rec = dict(w=w, h=h, D=D, seed=seed, kind=str(kind), colour=int(colour), disp_mv=mv, disp_h=hz, disp_v=vt,
                    input_sha=np.array([sha(v) for v in views]))
         for mode in range(3):
             t = ref.multistereo_taps(pads, D, mode)

@@ -133,6 +133,21 @@ def _views_ptrs(views):
     return arr, keep
 
 
+def _views_ptrs_strided(views):
+    """Pointers + the common row stride (cv::Mat::step) of views whose rows are dense but may be padded -- an ROI of a
+    larger image, what `Mat(rect)` hands the reference class. Falls back to dense copies when the views do not share
+    one such stride."""
+    vs = [np.asarray(v) for v in views]
+    ch = 3 if vs[0].ndim == 3 else 1
+    inner = (ch, 1) if ch == 3 else (1,)
+    step = vs[0].strides[0]
+    if all(v.dtype == np.uint8 and v.strides[1:] == inner and v.strides[0] == step and step >= v.shape[1] * ch for v in vs):
+        arr = (_u8p * len(vs))(*[C.cast(v.ctypes.data, _u8p) for v in vs])
+        return arr, vs, step
+    arr, keep = _views_ptrs(vs)
+    return arr, keep, vs[0].shape[1] * ch
+
+
 class Engine:
     """One context on one GPU: ``n_slots`` rigs in flight, sized for rigs up to max_w x max_h x max_disp."""
 
@@ -183,11 +198,11 @@ class Engine:
     def compute(self, views, disp_count: int, mode_mask: int = MODE_ALL, want_raw: bool = False):
         """views: center, right, top, left, bottom (H x W x 3 BGR or H x W grey, uint8). Returns [mv, horiz, vert]."""
         w, h, ch = self._shape(views)
-        arr, keep = _views_ptrs(views)
+        arr, keep, step = _views_ptrs_strided(views)
         outs = [np.zeros((h, w), np.uint16) if (mode_mask >> k) & 1 else None for k in range(3)]
         oarr = (_u16p * 3)(*[o.ctypes.data_as(_u16p) if o is not None else None for o in outs])
         raw = np.zeros((3, h + 2 * disp_count, w + 2 * disp_count), np.int16) if want_raw else None
-        self._chk(self.lib.sister_compute(self.ctx, arr, w, h, ch, w * ch, disp_count, mode_mask, oarr,
+        self._chk(self.lib.sister_compute(self.ctx, arr, w, h, ch, step, disp_count, mode_mask, oarr,
                                           raw.ctypes.data_as(_i16p) if want_raw else None))
         return (outs, raw) if want_raw else outs
 
@@ -196,11 +211,11 @@ class Engine:
         n = len(rigs)
         w, h, ch = self._shape(rigs[0])
         flat = [v for rig in rigs for v in rig]
-        arr, keep = _views_ptrs(flat)
+        arr, keep, step = _views_ptrs_strided(flat)
         if outs is None:
             outs = [[np.zeros((h, w), np.uint16) if (mode_mask >> k) & 1 else None for k in range(3)] for _ in range(n)]
         oarr = (_u16p * (3 * n))(*[o.ctypes.data_as(_u16p) if o is not None else None for rig in outs for o in rig])
-        self._chk(self.lib.sister_compute_batch(self.ctx, n, arr, w, h, ch, w * ch, disp_count, mode_mask, oarr))
+        self._chk(self.lib.sister_compute_batch(self.ctx, n, arr, w, h, ch, step, disp_count, mode_mask, oarr))
         return outs
 
     def submit(self, slot: int, views, disp_count: int, mode_mask: int = MODE_ALL):

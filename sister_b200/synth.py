@@ -67,8 +67,12 @@ def disparity_field(h: int, w: int, disp_count: int, kind: str = "smooth") -> np
     return np.clip(np.rint(d), 0, disp_count - 1).astype(np.int64)
 
 
-def make_rig(w: int, h: int, disp_count: int, seed: int = 1234, kind="smooth", noise: int = 3, channels: int = 1):
-    """Return the 5 views (center, right, top, left, bottom) as uint8 arrays H x W (or H x W x 3, grey replicated)."""
+def make_rig(w: int, h: int, disp_count: int, seed: int = 1234, kind="smooth", noise: int = 3, channels: int = 1, colour: bool = False):
+    """Return the 5 views (center, right, top, left, bottom) as uint8 arrays H x W (or H x W x 3).
+
+    channels = 3 replicates grey to B = G = R unless ``colour`` is set: then the three channels of every view get their own
+    gain, offset and noise stream (B != G != R almost everywhere), so that the fixed-point BGR2GRAY of hpp:29-33 is
+    actually exercised and a swapped or mis-weighted channel changes the result."""
     m = disp_count  # margin so that every shifted lookup stays inside the texture
     T = texture(h + 2 * m, w + 2 * m, seed)
     d = disparity_field(h, w, disp_count, kind)
@@ -82,7 +86,13 @@ def make_rig(w: int, h: int, disp_count: int, seed: int = 1234, kind="smooth", n
             n = (splitmix64(seed * 7919 + 13 * (k + 1), h * w) % np.uint64(2 * noise + 1)).astype(np.int32).reshape(h, w) - noise
             v = np.clip(v.astype(np.int32) + n, 0, 255).astype(np.uint8)
         v = np.ascontiguousarray(v)
-        if channels == 3:
+        if channels == 3 and colour:
+            chans = []
+            for c, (gain_num, offs) in enumerate(((3, 40), (4, 0), (5, -30))):  # B, G, R: gain / 4, offset
+                nc = (splitmix64(seed * 104729 + 31 * (k + 1) + 7 * (c + 1), h * w) % np.uint64(9)).astype(np.int32).reshape(h, w) - 4
+                chans.append(np.clip(v.astype(np.int32) * gain_num // 4 + offs + nc, 0, 255).astype(np.uint8))
+            v = np.ascontiguousarray(np.stack(chans, axis=2))
+        elif channels == 3:
             v = np.ascontiguousarray(np.repeat(v[:, :, None], 3, axis=2))
         out.append(v)
     return out

@@ -33,3 +33,19 @@ def ref_lib():
 
 def golden_rigs():
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith("rig_") and f.endswith(".npz"))
+
+
+def golden_views(g, channels=3):
+    """The rig a golden record was generated from (scripts/gen_golden.py): seeds, not pixels, are stored."""
+    from sister_b200.synth import make_rig
+    colour = bool(int(g["colour"])) if "colour" in g.files else False
+    return make_rig(int(g["w"]), int(g["h"]), int(g["D"]), seed=int(g["seed"]), kind=str(g["kind"]), channels=channels, colour=colour)
+
+
+def grey_of(view):
+    """OpenCV-4 BGR2GRAY (hpp:29-33), numpy: what a caller who converts first would pass as 1 channel."""
+    import numpy as np
+    if view.ndim == 2:
+        return view
+    v = view.astype(np.int64)
+    return ((3735 * v[:, :, 0] + 19235 * v[:, :, 1] + 9798 * v[:, :, 2] + 16384) >> 15).astype(np.uint8)

@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT
+from conftest import GOLDEN, ROOT, golden_views, grey_of
 from sister_b200.synth import VIEW_NAMES, make_rig
 
 import sister_b200
@@ -63,7 +63,7 @@ def test_cli_outputs(cli, tmp_path):
     cv2 = pytest.importorskip("cv2")
     g = np.load(os.path.join(GOLDEN, "rig_128x96_d64.npz"))
     w, h, D = int(g["w"]), int(g["h"]), int(g["D"])
-    views = make_rig(w, h, D, seed=int(g["seed"]), kind=str(g["kind"]), channels=3)
+    views = golden_views(g)
     folder = str(tmp_path) + "/"
     write_rig(folder, views)
     p = subprocess.run([cli, folder, str(D)], capture_output=True, text=True)

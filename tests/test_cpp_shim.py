@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT
+from conftest import GOLDEN, ROOT, golden_views, grey_of
 from sister_b200.synth import make_rig
 
 import sister_b200
@@ -28,7 +28,7 @@ def driver():
 def run_driver(exe, tmp_path, name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     w, h, D = int(g["w"]), int(g["h"]), int(g["D"])
-    views = make_rig(w, h, D, seed=int(g["seed"]), kind=str(g["kind"]), channels=3)
+    views = golden_views(g)
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     np.stack(views).astype(np.uint8).tofile(fin)
     p = subprocess.run([exe, fin, fout, str(w), str(h), str(D)], capture_output=True, text=True)

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, golden_rigs
+from conftest import GOLDEN, golden_rigs, golden_views, grey_of
 from sister_b200.synth import make_rig
 
 pytestmark = pytest.mark.gpu
@@ -26,22 +26,25 @@ def engine():
 def test_golden_rigs(engine, name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     w, h, D = int(g["w"]), int(g["h"]), int(g["D"])
-    views = make_rig(w, h, D, seed=int(g["seed"]), kind=str(g["kind"]), channels=3)
+    views = golden_views(g)
     outs, raw = engine.compute(views, D, want_raw=True)
     for m, key in enumerate(("disp_mv", "disp_h", "disp_v")):
         assert (raw[m] == g[f"raw_disp_m{m}"]).all(), f"raw disparity differs, mode {m}: {(raw[m] != g[f'raw_disp_m{m}']).sum()} px"
         assert (outs[m] == g[key]).all(), key
     # grey input == grey replicated to BGR; single mode leaves the other outputs untouched
-    outs1 = engine.compute([v[:, :, 0] for v in views], D, mode_mask=1)
+    outs1 = engine.compute([grey_of(v) for v in views], D, mode_mask=1)
     assert (outs1[0] == g["disp_mv"]).all() and outs1[1] is None and outs1[2] is None
     outs2 = engine.compute(views, D, mode_mask=6)
     assert outs2[0] is None and (outs2[1] == g["disp_h"]).all() and (outs2[2] == g["disp_v"]).all()
 
 
-@pytest.mark.parametrize("w,h,D,kind,seed", [(96, 64, 32, "smooth", 11), (40, 56, 8, "plane", 12), (72, 60, 24, "smooth", 13),
-                                                 (48, 40, 96, "smooth", 14)])  # D = 32, 96: lane-interleaved cells (4 chains per warp)
-def test_every_stage_against_oracle(engine, oracle_lib, w, h, D, kind, seed):
-    views = make_rig(w, h, D, seed=seed, kind=kind, channels=3)
+@pytest.mark.parametrize("w,h,D,kind,seed,colour", [(96, 64, 32, "smooth", 11, False), (40, 56, 8, "plane", 12, False), (72, 60, 24, "smooth", 13, False),
+                                                        (48, 40, 96, "smooth", 14, False),  # D = 32, 96: lane-interleaved cells (4 chains per warp)
+                                                        (88, 72, 40, "smooth", 15, True), (56, 44, 16, "smooth", 16, True)])  # B != G != R: hpp:29-33
+def test_every_stage_against_oracle(engine, oracle_lib, w, h, D, kind, seed, colour):
+    views = make_rig(w, h, D, seed=seed, kind=kind, channels=3, colour=colour)
+    if colour:
+        assert all((v[:, :, 0] != v[:, :, 2]).mean() > 0.5 for v in views)
     wp, hp = w + 2 * D, h + 2 * D
     px = wp * hp
     pads = [oracle_lib.pad_replicate(oracle_lib.grey_bgr(v), D) for v in views]
@@ -119,7 +122,7 @@ def test_batch_equals_single_and_is_deterministic(engine):
 def test_reference_class_mirror(engine):
     import sister_b200
     g = np.load(os.path.join(GOLDEN, "rig_64x48_d16.npz"))
-    views = make_rig(64, 48, 16, seed=int(g["seed"]), kind=str(g["kind"]), channels=3)
+    views = golden_views(g)
     s = sister_b200.SisterMultiviewDisparities(*views, engine=engine)
     mv, hz, vt = s.compute_disparities(16)
     assert (mv == g["disp_mv"]).all() and (hz == g["disp_h"]).all() and (vt == g["disp_v"]).all()
@@ -143,7 +146,7 @@ def test_crop_only_aggregation_reproduces_golden_maps(name):
     import sister_b200
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     w, h, D = int(g["w"]), int(g["h"]), int(g["D"])
-    views = make_rig(w, h, D, seed=int(g["seed"]), kind=str(g["kind"]), channels=3)
+    views = golden_views(g)
     with sister_b200.Engine(w, h, D, n_slots=2) as eng:  # no taps: crop only
         outs = eng.compute(views, D)
         assert (outs[0] == g["disp_mv"]).all() and (outs[1] == g["disp_h"]).all() and (outs[2] == g["disp_v"]).all()
@@ -239,7 +242,7 @@ def test_pinned_and_strided_inputs(engine):
     """Views in page-locked memory are copied to the device directly, pageable or row-padded ones are staged: same maps."""
     g = np.load(os.path.join(GOLDEN, "rig_96x64_d32.npz"))
     w, h, D = int(g["w"]), int(g["h"]), int(g["D"])
-    views = make_rig(w, h, D, seed=int(g["seed"]), kind=str(g["kind"]), channels=3)
+    views = golden_views(g)
     pinned = engine.host_array((5, h, w, 3), np.uint8)
     for k in range(5):
         pinned[k] = views[k]
@@ -247,3 +250,56 @@ def test_pinned_and_strided_inputs(engine):
     assert (a == g["disp_mv"]).all()
     batch = engine.compute_batch([[pinned[k] for k in range(5)]] * 3, D, mode_mask=1)
     assert all((b[0] == g["disp_mv"]).all() for b in batch)
+    # row-padded views (cv::Mat::step > w * channels): regions of interest of larger images, pageable and page-locked
+    for big in (np.full((5, h + 9, w + 23, 3), 77, np.uint8), engine.host_array((5, h + 9, w + 23, 3), np.uint8)):
+        big[:] = 77
+        roi = [big[k, 4:4 + h, 11:11 + w] for k in range(5)]
+        for k in range(5):
+            roi[k][:] = views[k]
+        assert roi[0].strides[0] == (w + 23) * 3 and not roi[0].flags["C_CONTIGUOUS"]
+        c = engine.compute(roi, D, mode_mask=1)[0]
+        assert (c == g["disp_mv"]).all(), "row-padded BGR views"
+        batch = engine.compute_batch([roi, roi], D, mode_mask=1)
+        assert all((b[0] == g["disp_mv"]).all() for b in batch)
+    bigg = np.zeros((5, h + 2, w + 40), np.uint8)
+    roig = [bigg[k, 1:1 + h, 8:8 + w] for k in range(5)]
+    for k in range(5):
+        roig[k][:] = grey_of(views[k])
+    assert (engine.compute(roig, D, mode_mask=1)[0] == g["disp_mv"]).all(), "row-padded grey views"
+
+
+def test_config2_against_oracle(oracle_lib):
+    """BASELINE.json configs[1], the headline shape: 1280x960, D = 192, the multiview map (doMultiStereo mode 0,
+    hpp:152-295) -- raw padded disparity and encoded map against the reference itself when oracle/_ref is present (it travels
+    with the repo), else against the plain-C port."""
+    import oracle
+    import sister_b200
+    W, H, D = 1280, 960, 192
+    views = make_rig(W, H, D, seed=1234, channels=1)
+    with sister_b200.Engine(W, H, D, n_slots=1) as eng:
+        outs, raw = eng.compute(views, D, mode_mask=1, want_raw=True)
+        crop_only = eng.compute(views, D, mode_mask=1)[0]
+    pads = [oracle_lib.pad_replicate(v, D) for v in views]
+    if os.path.exists(oracle.REF_SO):
+        ref_raw = oracle.Ref().multistereo_taps(pads, D, mode=0, want_volumes=False)["disp"]
+    else:
+        ref_raw = oracle_lib.multistereo(pads, D, 0, want_volumes=False)["disp"]
+    assert (raw[0] == ref_raw).all(), f"{(raw[0] != ref_raw).sum()} padded pixels differ"
+    ref_map = oracle_lib.encode_crop(ref_raw, D)
+    assert (outs[0] == ref_map).all() and (crop_only == ref_map).all()
+
+
+def test_output_saturation_above_258(oracle_lib):
+    """hpp:116-118: the uint16 map is disparity * 255 with saturation, so every disparity >= 258 reads 65535. A rig whose
+    true disparity is 270 at D = 288 (beyond the reference's own D < 272 limit, postprocess.cpp:193: the widened port is
+    the check) reaches it in the horizontal map."""
+    import sister_b200
+    w, h, D = 320, 16, 288
+    views = make_rig(w, h, D, seed=31, kind=270, channels=1)
+    with sister_b200.Engine(w, h, D, n_slots=1) as eng:
+        outs, raw = eng.compute(views, D, mode_mask=2, want_raw=True)
+    ref, ref_raw = oracle_lib.compute_disparities(views, D, mode_mask=2, want_raw=True)
+    assert (raw[1] == ref_raw[1]).all()
+    assert (outs[1] == ref[1]).all()
+    crop = raw[1][D:D + h, D:D + w]
+    assert (crop >= 258).sum() > 500 and (outs[1][crop >= 258] == 65535).all() and (outs[1][crop < 258] < 65535).all()

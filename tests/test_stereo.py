@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, golden_views, grey_of
 from sister_b200.synth import make_rig
 
 G = np.load(os.path.join(GOLDEN, "stereo_pairs.npz"))
@@ -64,7 +64,7 @@ def test_gpu_sgm_with_invalid_cost_marker():
 def test_gpu_two_view_then_five_view_on_one_context(oracle_lib):
     import sister_b200
     g = np.load(os.path.join(GOLDEN, "rig_64x48_d16.npz"))
-    views = make_rig(64, 48, 16, seed=int(g["seed"]), kind=str(g["kind"]), channels=3)
+    views = golden_views(g)
     c, r, D = pair(3)
     with sister_b200.Engine(96, 112, 16, n_slots=1) as eng:
         a = eng.compute(views, 16)
