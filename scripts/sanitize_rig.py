@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""One small rig through every kernel of the path -- the 5-view call (3 modes, crop-only and whole frame), the batch
+pipeline, the two-view path, an SGM stage call and a 3-band run on one GPU -- for compute-sanitizer
+(scripts/sanitize.sh runs it under memcheck, racecheck, initcheck and synccheck)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import sister_b200  # noqa: E402
+from sister_b200.synth import make_rig  # noqa: E402
+
+w, h, D = 96, 64, 32
+views = make_rig(w, h, D, seed=42, channels=3, colour=True)
+with sister_b200.Engine(w, h, D, n_slots=3) as eng:
+    a = eng.compute(views, D)
+    b, raw = eng.compute(views, D, want_raw=True)
+    assert all((x == y).all() for x, y in zip(a, b))
+    batch = eng.compute_batch([views] * 4, D, mode_mask=1)
+    assert all((r[0] == a[0]).all() for r in batch)
+    g = [v[:, :, 1].copy() for v in views]
+    eng.stereo(g[0], g[1], D)
+    vol = np.random.default_rng(1).integers(0, 253, (16, 24, 40), dtype=np.uint8)
+    eng.test_sgm(vol)
+    if "--bands" in sys.argv:
+        from sister_b200.bands import EngineBandWorker, as_uint16, run_bands_in_process
+        workers = [EngineBandWorker(eng, views, D, r, 3, mode=0, slot=r) for r in range(3)]
+        rows = run_bands_in_process(workers)
+        got = np.concatenate([as_uint16(r) for r in rows], axis=0)
+        assert (got == a[0]).all()
+print("sanitize_rig ok")

@@ -73,6 +73,14 @@ int fail_cuda(sister_ctx *ctx, cudaError_t e, const char *what)
         if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);       \
     } while (0)
 
+// a launcher's own set-up failure (shared-memory opt-in, table allocation), reported once
+cudaError_t take_launch_error(sister_ctx *ctx)
+{
+    const cudaError_t e = ctx->lc.err;
+    ctx->lc.err = cudaSuccess;
+    return e;
+}
+
 int check_shape(sister_ctx *ctx, int w, int h, int D, Dims &d)
 {
     if (w <= 0 || h <= 0 || D <= 0) { ctx->err = "non-positive size"; return SISTER_E_ARG; }
@@ -119,7 +127,8 @@ int run_pipeline(sister_ctx *ctx, Slot &s, const uint8_t *const in_views[5], int
     s.n_ev = 0;
     int before[16];
     memcpy(before, ctx->lc.stage, sizeof(before));
-    SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
+    // the status word ACCUMULATES (kernels atomicOr into it) over every submit queued on the slot until finish_slot has
+    // read and cleared it: a bit raised by an earlier rig is not overwritten by a later one
     const unsigned view_mask = (mode_mask & SISTER_MODE_MULTIVIEW) ? 0xFu
                                : (((mode_mask & SISTER_MODE_HORIZONTAL) ? 0x3u : 0u) | ((mode_mask & SISTER_MODE_VERTICAL) ? 0xCu : 0u));
     // the 5 views may live anywhere on the device: express them relative to view 0 when they are equally spaced,
@@ -154,6 +163,7 @@ int run_pipeline(sister_ctx *ctx, Slot &s, const uint8_t *const in_views[5], int
     }
     SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
     SCK(cudaGetLastError());
+    SCK(take_launch_error(ctx));
     for (int k = 0; k < SISTER_STAGE_COUNT; k++) s.stage_launches[k] = ctx->lc.stage[k] - before[k];
     s.dims = d;
     s.mode_mask = mode_mask;
@@ -188,6 +198,8 @@ int finish_slot(sister_ctx *ctx, Slot &s)
         char buf[96];
         snprintf(buf, sizeof buf, "kernel invariant violated, status bits 0x%x", *s.h_status);
         ctx->err = buf;
+        *s.h_status = 0;
+        cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st); // reported: start the next rig from a clean word
         return SISTER_E_INTERNAL;
     }
     return SISTER_OK;
@@ -252,6 +264,7 @@ int sister_create(sister_ctx **out, int device, int max_w, int max_h, int max_di
         A((void **)&s.d_status, sizeof(int)); H((void **)&s.h_status, sizeof(int));
         if (e != cudaSuccess) { rc = fail_cuda(nullptr, e, "alloc"); return bail(rc); }
         *s.h_status = 0;
+        cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st);
         cudaMemsetAsync(s.d_masks, 0, 4 * px, s.st);
         cudaMemsetAsync(s.d_raw, 0, 3 * px * 2, s.st);
     }
@@ -414,7 +427,6 @@ int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev
         if (views_dev[k] - views_dev[k - 1] != stride) { ctx->err = "device views must be equally spaced"; return SISTER_E_ARG; }
     if (stride <= 0) { ctx->err = "device views must be in ascending address order"; return SISTER_E_ARG; }
     const unsigned vm = mode == 0 ? 0xFu : mode == 1 ? 0x3u : 0xCu; // hpp:262-276
-    SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
     // staging, census, raw-cost WTA and the masks need neighbours far outside the band (D rows for the vertical views,
     // the whole map for the recursive median): every band computes them for the whole frame; the volumes -- fused cost,
     // path bytes, i.e. all the memory and most of the time -- exist for the band's rows only
@@ -425,6 +437,7 @@ int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev
     launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused, s.d_status, s.st, ctx->lc, band_row0, band_row1);
     launch_sgm_band(0, s.d_fused, d, band_row0, band_row1, nullptr, nullptr, s.d_paths, nullptr, nullptr, s.st, ctx->lc);
     SCK(cudaGetLastError());
+    SCK(take_launch_error(ctx));
     s.dims = d;
     s.mode_mask = 1u << mode;
     s.full_frame = false;
@@ -440,8 +453,14 @@ int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *sta
     Slot &s = ctx->slots[slot];
     if (pass < 0 || pass > 1 || s.band_r1 <= s.band_r0) { ctx->err = "sister_band_submit first; pass is 0 or 1"; return SISTER_E_ARG; }
     SCK(cudaSetDevice(ctx->device));
+    // a band that is not the first of its pass continues chains: without the neighbour's state they would silently restart
+    const bool first_of_pass = pass == 0 ? s.band_r0 == 0 : s.band_r1 == s.dims.Hp;
+    const bool last_of_pass = pass == 0 ? s.band_r1 == s.dims.Hp : s.band_r0 == 0;
+    if (!first_of_pass && !state_in_dev) { ctx->err = "state_in_dev is NULL but the band is not the first of this pass"; return SISTER_E_ARG; }
+    if (!last_of_pass && !state_out_dev) { ctx->err = "state_out_dev is NULL but the band is not the last of this pass"; return SISTER_E_ARG; }
     launch_sgm_band(1 + pass, s.d_fused, s.dims, s.band_r0, s.band_r1, state_in_dev, state_out_dev, s.d_paths, nullptr, nullptr, s.st, ctx->lc);
     SCK(cudaGetLastError());
+    SCK(take_launch_error(ctx));
     return SISTER_OK;
 }
 
@@ -706,7 +725,10 @@ int sister_stereo(sister_ctx *ctx, const uint8_t *center, const uint8_t *side, i
     if (!ctx->taps) { SCK(cudaFree(s.d_sum)); s.d_sum = nullptr; }
     s.dims = d;
     s.full_frame = true;
-    if (*s.h_status & ~kStatusFusedOverflow) { ctx->err = "kernel invariant violated"; return SISTER_E_INTERNAL; }
+    const int bits = *s.h_status; // the word accumulates (run_pipeline): leave it clean for the next submit on this slot
+    *s.h_status = 0;
+    SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
+    if (bits & ~kStatusFusedOverflow) { ctx->err = "kernel invariant violated"; return SISTER_E_INTERNAL; }
     std::vector<int16_t> tmp(px);
     SCK(cudaMemcpy(tmp.data(), s.d_lr, px * 2, cudaMemcpyDeviceToHost));
     for (size_t k = 0; k < px; k++) out_left[k] = (float)tmp[k];
@@ -748,7 +770,10 @@ int sister_test_sgm(sister_ctx *ctx, const uint8_t *fused, int w, int h, int dis
     if (disp) SCK(cudaMemcpy(disp, s.d_raw, (size_t)d.px * 2, cudaMemcpyDeviceToHost));
     if (!ctx->taps) { SCK(cudaFree(s.d_sum)); s.d_sum = nullptr; }
     s.dims = d;
-    return *s.h_status ? SISTER_E_INTERNAL : SISTER_OK;
+    const int bits = *s.h_status;
+    *s.h_status = 0;
+    SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
+    return bits ? SISTER_E_INTERNAL : SISTER_OK;
 }
 
 } // extern "C"

@@ -1,14 +1,39 @@
 // Host-side launch wrappers of the sm_100a kernels (definitions in stage.cu / match.cu / sgm.cu).
 #pragma once
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace sister {
+
+// Opt a kernel in to `bytes` of dynamic shared memory (above the 48 KB default). cudaFuncSetAttribute applies to the
+// CURRENT device only, so the opt-in is remembered per (kernel, device): a second context on another GPU of the same
+// process gets its own (one context per GPU in one process is a supported set-up).
+inline cudaError_t optin_dynamic_smem(const void *kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair(kernel, dev);
+    const auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done[key] = bytes;
+    return e;
+}
 
 struct LaunchCounter {
     unsigned long long total = 0;
     int stage[16] = {0};
     int cur_stage = 0;
+    cudaError_t err = cudaSuccess; // first failure of a launcher's own set-up (allocation, attribute); checked by the caller
     inline void add(int n = 1) { total += n; stage[cur_stage] += n; }
+    inline void fail(cudaError_t e) { if (e != cudaSuccess && err == cudaSuccess) err = e; }
 };
 
 // ---- stage.cu ----

@@ -162,11 +162,7 @@ void launch_match_wta(const unsigned long long *census, const Dims &d, unsigned 
 {
     int m = d.Wp > d.Hp ? d.Wp : d.Hp;
     size_t smem = (size_t)m * (8 + 8 + 4);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_match_wta, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
-    }
+    lc.fail(optin_dynamic_smem((const void *)k_match_wta, smem));
     int warps = (m + 32 * kMatchK - 1) / (32 * kMatchK);
     if (warps > 13) warps = 13;
     dim3 grid(m, 4);
@@ -175,25 +171,6 @@ void launch_match_wta(const unsigned long long *census, const Dims &d, unsigned 
 }
 
 // ---------------------------------------------------------------------------------------------- median
-
-__device__ __forceinline__ void sort2(int &a, int &b)
-{
-    int lo = min(a, b), hi = max(a, b);
-    a = lo; b = hi;
-}
-
-// the 19-exchange network of postprocess.cpp:52-58
-__device__ __forceinline__ int median9(int v0, int v1, int v2, int v3, int v4, int v5, int v6, int v7, int v8)
-{
-    sort2(v1, v2); sort2(v4, v5); sort2(v7, v8);
-    sort2(v0, v1); sort2(v3, v4); sort2(v6, v7);
-    sort2(v1, v2); sort2(v4, v5); sort2(v7, v8);
-    sort2(v0, v3); sort2(v5, v8); sort2(v4, v7);
-    sort2(v3, v6); sort2(v1, v4); sort2(v2, v5);
-    sort2(v4, v7); sort2(v4, v2); sort2(v6, v4);
-    sort2(v4, v2);
-    return v4;
-}
 
 // Median of nine on two pixels at once (packed s16x2). The value of a median does not depend on the network that finds
 // it, so instead of the 19 compare-exchanges of postprocess.cpp:52-58 (38 min / max): sort the three columns, then
@@ -407,12 +384,9 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
                             int16_t *medR, int16_t *lr_final, uint8_t *masks, cudaStream_t st, LaunchCounter &lc)
 {
     int m = d.Wp > d.Hp ? d.Wp : d.Hp;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_median, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
-    }
-    k_median<<<8, 1024, (size_t)(kMedRing + 4) * m * sizeof(int16_t), st>>>(wtaL, wtaR, d, view_mask, medL, medR);
+    const size_t med_smem = (size_t)(kMedRing + 4) * m * sizeof(int16_t);
+    lc.fail(optin_dynamic_smem((const void *)k_median, med_smem));
+    k_median<<<8, 1024, med_smem, st>>>(wtaL, wtaR, d, view_mask, medL, medR);
     lc.add();
     dim3 grid((m + 255) / 256, m, 4);
     k_lrc_mask<<<grid, 256, 0, st>>>(medL, medR, d, view_mask, lr_final, masks);
@@ -656,25 +630,21 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
 
 template <int T, int NK, int ORDER>
 static void launch_fuse_o(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
-                          int *status, cudaStream_t st, int row_lo, int row_hi)
+                          int *status, cudaStream_t st, int row_lo, int row_hi, LaunchCounter &lc)
 {
     const size_t smem = (size_t)4 * T * (T + d.D) * 8 + (size_t)4 * T * T * 8 + T * T;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_fuse<T, NK, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_done = true;
-    }
+    lc.fail(optin_dynamic_smem((const void *)k_fuse<T, NK, ORDER>, smem));
     dim3 grid((d.Wp + T - 1) / T, (row_hi - row_lo + T - 1) / T);
     k_fuse<T, NK, ORDER><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, status, row_lo);
 }
 
 template <int T, int NK>
 static void launch_fuse_t(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
-                          int *status, cudaStream_t st, int row_lo, int row_hi)
+                          int *status, cudaStream_t st, int row_lo, int row_hi, LaunchCounter &lc)
 {
-    if (NK > 0 && d.interleaved && d.lpc == 16 && d.nr == NK) launch_fuse_o<T, NK, (NK > 0 ? 2 : 0)>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi);
-    else if (NK > 0 && !d.interleaved) launch_fuse_o<T, NK, (NK > 0 ? 1 : 0)>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi);
-    else launch_fuse_o<T, NK, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi);
+    if (NK > 0 && d.interleaved && d.lpc == 16 && d.nr == NK) launch_fuse_o<T, NK, (NK > 0 ? 2 : 0)>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc);
+    else if (NK > 0 && !d.interleaved) launch_fuse_o<T, NK, (NK > 0 ? 1 : 0)>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc);
+    else launch_fuse_o<T, NK, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc);
 }
 
 void launch_fuse(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
@@ -685,17 +655,17 @@ void launch_fuse(const unsigned long long *census, const uint8_t *masks, const D
     // 16 x 16 tiles while two blocks fit an SM (D <= 200), else 8 x 8
     if (d.D <= 200) {
         switch (d.D) {
-        case 64: launch_fuse_t<16, 2>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
-        case 128: launch_fuse_t<16, 4>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
-        case 192: launch_fuse_t<16, 6>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
-        default: launch_fuse_t<16, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
+        case 64: launch_fuse_t<16, 2>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
+        case 128: launch_fuse_t<16, 4>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
+        case 192: launch_fuse_t<16, 6>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
+        default: launch_fuse_t<16, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
         }
     } else {
         switch (d.D) {
-        case 256: launch_fuse_t<8, 8>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
-        case 384: launch_fuse_t<8, 12>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
-        case 512: launch_fuse_t<8, 16>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
-        default: launch_fuse_t<8, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi); break;
+        case 256: launch_fuse_t<8, 8>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
+        case 384: launch_fuse_t<8, 12>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
+        case 512: launch_fuse_t<8, 16>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
+        default: launch_fuse_t<8, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
         }
     }
     lc.add();

@@ -775,8 +775,14 @@ void launch_wta_right_sum(const uint16_t *sum, const Dims &d, int16_t *outR, cud
 // measured on B200 at D = 192, two chains per warp (twice the warps) beat four chains per warp by 20 %.
 void set_cell_order(Dims &d)
 {
-    static int lpc8_max = -1; // measurement aid: SISTER_DEBUG_LPC8_MAXD=<largest D that runs four chains per warp>
-    if (lpc8_max < 0) { const char *e = getenv("SISTER_DEBUG_LPC8_MAXD"); lpc8_max = e ? atoi(e) : 128; }
+    // measurement aid, only in builds with -DSISTER_DEBUG_HOOKS: SISTER_DEBUG_LPC8_MAXD=<largest D that runs four chains per warp>
+    static int lpc8_max = -1;
+    if (lpc8_max < 0) {
+        lpc8_max = 128;
+#ifdef SISTER_DEBUG_HOOKS
+        if (const char *e = getenv("SISTER_DEBUG_LPC8_MAXD")) lpc8_max = atoi(e);
+#endif
+    }
     d.lpc = (d.D <= lpc8_max && d.D <= 192) ? 8 : 16;
     d.lpc_shift = d.lpc == 8 ? 3 : 4;
     d.nr = 2 * ((d.D + 4 * d.lpc - 1) / (4 * d.lpc));
@@ -786,9 +792,13 @@ void set_cell_order(Dims &d)
     d.interleaved = (d.D == 2 * d.lpc * d.nr && d.nr % 4 == 2) ? 1 : 0;
 }
 
-// measurement aid: SISTER_DEBUG_PATH_KINDS=<bit mask of chain kinds to run> (results are then incomplete)
+// measurement aid, only in builds with -DSISTER_DEBUG_HOOKS (the shipped library never reads the environment):
+// SISTER_DEBUG_PATH_KINDS=<bit mask of chain kinds to run> (results are then incomplete)
 static unsigned debug_section_mask()
 {
+#ifndef SISTER_DEBUG_HOOKS
+    return 0x1FFu;
+#endif
     static int m = -1;
     if (m < 0) {
         const char *e = getenv("SISTER_DEBUG_PATH_KINDS");
@@ -808,7 +818,7 @@ struct WarpOrder {
     int *dev = nullptr;
     int n = 0;
 };
-static const WarpOrder &warp_order_for(const Sections &sec, unsigned section_mask, int cpw)
+static const WarpOrder &warp_order_for(const Sections &sec, unsigned section_mask, int cpw, cudaStream_t st, LaunchCounter &lc)
 {
     struct Key {
         long long o[10];
@@ -849,30 +859,35 @@ static const WarpOrder &warp_order_for(const Sections &sec, unsigned section_mas
     WarpOrder wo;
     wo.n = (int)order.size();
     if (wo.n > 0) {
-        cudaMalloc((void **)&wo.dev, order.size() * sizeof(int));
-        cudaMemcpy(wo.dev, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice);
+        // built once per (geometry, device); ordered before the first kernel that reads it by the stream it is copied on
+        cudaError_t e = cudaMalloc((void **)&wo.dev, order.size() * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(wo.dev, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st); // `order` dies with this call; other streams may use the table next
+        if (e != cudaSuccess) {
+            lc.fail(e);
+            if (wo.dev) cudaFree(wo.dev);
+            static const WarpOrder none;
+            return none; // not cached: the next launch tries again
+        }
     }
     return cache.emplace(key, wo).first->second;
 }
 
 template <int NR, int LPC, bool FULL, bool IL>
-static void launch_paths(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol, cudaStream_t st)
+static void launch_paths(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol, cudaStream_t st, LaunchCounter &lc)
 {
     constexpr int CPW = 32 / LPC;
     const Sections sec = chain_sections(d, roi, band, CPW);
-    const WarpOrder &wo = warp_order_for(sec, section_mask, CPW);
+    const WarpOrder &wo = warp_order_for(sec, section_mask, CPW, st, lc);
     if (wo.n == 0) return;
     const size_t smem = FULL ? (size_t)kChainWarps * kRing * CPW * d.D : 0; // the cost ring of run_chain_ring
-    if (smem > 48 * 1024) {
-        static bool attr_done = false; // per instantiation
-        if (!attr_done) { cudaFuncSetAttribute(k_sgm_paths<NR, LPC, FULL, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
-    }
+    if (smem > 48 * 1024) lc.fail(optin_dynamic_smem((const void *)k_sgm_paths<NR, LPC, FULL, IL>, smem));
     k_sgm_paths<NR, LPC, FULL, IL><<<(unsigned)((wo.n + kChainWarps - 1) / kChainWarps), kChainWarps * 32, smem, st>>>(fused, d, roi, band, sec, qvol,
                                                                                                             section_mask, wo.dev, wo.n, 1u);
 }
 
 template <int LPC, int NRMAX>
-static void launch_paths_lpc(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol, cudaStream_t st)
+static void launch_paths_lpc(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol, cudaStream_t st, LaunchCounter &lc)
 {
     const int nr = d.nr;
     const bool full = d.D == 2 * LPC * nr;
@@ -880,10 +895,10 @@ static void launch_paths_lpc(const uint8_t *fused, const Dims &d, const Roi &roi
     case N:                                                                                     \
         if constexpr (N <= NRMAX) {                                                             \
             if constexpr (N % 4 == 2) {                                                         \
-                if (d.interleaved) { launch_paths<N, LPC, true, true>(fused, d, roi, band, section_mask, qvol, st); break; } \
+                if (d.interleaved) { launch_paths<N, LPC, true, true>(fused, d, roi, band, section_mask, qvol, st, lc); break; } \
             }                                                                                   \
-            if (full) launch_paths<N, LPC, true, false>(fused, d, roi, band, section_mask, qvol, st);                    \
-            else launch_paths<N, LPC, false, false>(fused, d, roi, band, section_mask, qvol, st);                        \
+            if (full) launch_paths<N, LPC, true, false>(fused, d, roi, band, section_mask, qvol, st, lc);                    \
+            else launch_paths<N, LPC, false, false>(fused, d, roi, band, section_mask, qvol, st, lc);                        \
         }                                                                                       \
         break;
     switch (nr) {
@@ -902,10 +917,10 @@ static Roi make_roi(const Dims &d, bool full_frame)
 }
 
 static void launch_paths_any(const uint8_t *fused, const Dims &d, const Roi &roi, const Band &band, unsigned section_mask, uint8_t *qvol,
-                             cudaStream_t st)
+                             cudaStream_t st, LaunchCounter &lc)
 {
-    if (d.lpc == 8) launch_paths_lpc<8, 12>(fused, d, roi, band, section_mask, qvol, st); // four chains per warp
-    else launch_paths_lpc<16, 16>(fused, d, roi, band, section_mask, qvol, st);           // two (D <= 512, check_shape)
+    if (d.lpc == 8) launch_paths_lpc<8, 12>(fused, d, roi, band, section_mask, qvol, st, lc); // four chains per warp
+    else launch_paths_lpc<16, 16>(fused, d, roi, band, section_mask, qvol, st, lc);           // two (D <= 512, check_shape)
 }
 
 static void launch_final(const uint8_t *fused, const uint8_t *qvol, const Dims &d, const Roi &roi, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
@@ -927,7 +942,7 @@ void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, uint8_t *q
     Band band;
     band.b0 = 0; band.b1 = d.Hp;
     band.in[0] = band.in[1] = nullptr; band.out[0] = band.out[1] = nullptr;
-    launch_paths_any(fused, d, roi, band, debug_section_mask(), qvol, st);
+    launch_paths_any(fused, d, roi, band, debug_section_mask(), qvol, st, lc);
     lc.add();
     launch_final(fused, qvol, d, roi, sum, raw_disp, out, st);
     lc.add();
@@ -951,7 +966,7 @@ void launch_sgm_band(int what, const uint8_t *fused, const Dims &d, int band_r0,
     } else {
         if (what == 1) { band.in[0] = state_in; band.out[0] = state_out; }
         if (what == 2) { band.in[1] = state_in; band.out[1] = state_out; }
-        launch_paths_any(fused, d, roi, band, what == 0 ? 0x006u : what == 1 ? 0x038u : 0x1C0u, qvol, st);
+        launch_paths_any(fused, d, roi, band, what == 0 ? 0x006u : what == 1 ? 0x038u : 0x1C0u, qvol, st, lc);
     }
     lc.add();
 }

@@ -303,3 +303,44 @@ def test_output_saturation_above_258(oracle_lib):
     assert (outs[1] == ref[1]).all()
     crop = raw[1][D:D + h, D:D + w]
     assert (crop >= 258).sum() > 500 and (outs[1][crop >= 258] == 65535).all() and (outs[1][crop < 258] < 65535).all()
+
+
+def test_two_contexts_on_two_devices_in_one_process():
+    """One context per GPU inside ONE process: the shared-memory opt-ins of the kernels are per
+    device, so the second device must work like the first. Skips on a one-GPU box."""
+    import sister_b200
+    g = np.load(os.path.join(GOLDEN, "rig_128x96_d64.npz"))
+    views = golden_views(g)
+    w, h, D = int(g["w"]), int(g["h"]), int(g["D"])
+    try:
+        eng1 = sister_b200.Engine(1280, 960, 192, n_slots=1, device=1)
+    except sister_b200.SisterError as e:
+        if e.code == -5:
+            pytest.skip("one GPU")
+        raise
+    with eng1, sister_b200.Engine(1280, 960, 192, n_slots=1, device=0) as eng0:
+        for eng in (eng0, eng1, eng0):
+            outs = eng.compute(views, D)
+            assert (outs[0] == g["disp_mv"]).all() and (outs[1] == g["disp_h"]).all() and (outs[2] == g["disp_v"]).all()
+        # the headline shape needs the large opt-ins (k_fuse 115 KB) on both devices
+        plane = make_rig(1280, 960, 192, seed=7, kind="plane", noise=0, channels=1)
+        a = eng0.compute(plane, 192, mode_mask=1)[0]
+        b = eng1.compute(plane, 192, mode_mask=1)[0]
+        assert (a == b).all()
+
+
+def test_status_word_survives_queued_submits(engine):
+    """Several device submits queued on one slot before sister_sync share the slot's status word: it accumulates, and a
+    clean run leaves it clean (sister_sync returns OK and the next host submit is unaffected)."""
+    g = np.load(os.path.join(GOLDEN, "rig_64x48_d16.npz"))
+    views = golden_views(g)
+    rig = engine.upload_rig(views)
+    out = engine.dev_alloc(3 * 64 * 48 * 2)
+    for _ in range(3):
+        engine.submit_device(1, rig, 64, 48, 3, 16, 7, [out, out + 64 * 48 * 2, out + 2 * 64 * 48 * 2])
+    engine.sync(1)
+    got = np.zeros((3, 48, 64), np.uint16)
+    engine.dev_download(out, got)
+    assert (got[0] == g["disp_mv"]).all() and (got[1] == g["disp_h"]).all() and (got[2] == g["disp_v"]).all()
+    engine.dev_free(rig)
+    engine.dev_free(out)
