@@ -1,13 +1,17 @@
-"""Numpy stand-in for one row band of the aggregation (sister_b200/bands.py worker interface), built from the pieces of
-tests/sgm_spec.py. Test infrastructure only: it lets the CPU tests run the band schedule -- in one process and over
-world_size-2/3 gloo -- and prove that chains cut at band borders and continued from the neighbour's state give exactly
-the single-band result. The state a band hands over is the chain state AFTER its last row; the border-crossing rule is
-applied by the band that takes the next step (the CUDA kernel folds it into the state instead; each worker only has to
-agree with itself)."""
+"""Numpy stand-in for one row band of the aggregation (sister_b200/bands.py worker interface), built from the paired
+sweeps of tests/sgm_spec.py (the formulation sister_b200/csrc/sgm.cu implements). Test infrastructure only: it lets the
+CPU tests run the band schedule -- in one process and over world_size-2/3 gloo -- and prove that sweeps cut at band
+borders and continued from the neighbour's state give exactly the single-band result.
+
+State a band hands to the next band of a pass (3 * Wp * D bytes, include/sister_b200.h):
+    [0]  row sweep: the rider (diagonal path) states its LAST row left, one per step (column), in step order
+    [1]  column sweep: the carrier (vertical path) states of all its chains after the band's last row
+    [2]  column sweep: the rider (other diagonal) states of all its chains after the band's last row
+all clamped normalised vectors a(d) <= P2, one byte per disparity."""
 import numpy as np
 import torch
 
-from sgm_spec import P2, _step
+from sgm_spec import Sweep, run_sweep
 
 
 class NumpyBandWorker:
@@ -16,8 +20,8 @@ class NumpyBandWorker:
         self.D, self.H, self.W = D, H, W
         self.Hp, self.Wp = C.shape[:2]
         self.row0, self.row1 = row0, row1
-        self.Q = np.zeros((8, self.Hp, self.Wp, D), np.int64)
-        self.touched = np.zeros((self.Hp,), bool)
+        self.roi = (D, D + H, D, D + W)        # Rect(D, D, W, H), hpp:116-118
+        self.V = np.zeros((4, self.Hp, self.Wp, D), np.int64)
 
     def new_state(self):
         return torch.zeros(3 * self.Wp * self.D, dtype=torch.uint8)
@@ -26,45 +30,27 @@ class NumpyBandWorker:
         return max(self.row0, self.D), min(self.row1, self.D + self.H)
 
     def submit(self):
-        lo, hi = self._crop_rows()
-        self.touched[self.row0:self.row1] = True
-        if hi <= lo:
-            return
-        rr = np.arange(lo, hi)
-        for p, cols in ((0, range(0, self.Wp)), (1, range(self.Wp - 1, -1, -1))):
-            a = np.zeros((len(rr), self.D), np.int64)
-            for j in cols:
-                q, a = _step(a, self.C[rr, j])
-                self.Q[4 * p, rr, j] = q
+        pass  # every sweep carries a diagonal path: nothing of the aggregation is local to a band any more
 
     def vertical(self, p, state_in, want_out):
-        dj = 1 if p == 0 else -1
-        i1, j1, jl = (0, 0, self.Wp - 1) if p == 0 else (self.Hp - 1, self.Wp - 1, 0)
-        rows = range(self.row0, self.row1) if p == 0 else range(self.row1 - 1, self.row0 - 1, -1)
-        done = self.row0 if p == 0 else self.Hp - self.row1  # steps behind the chains when they enter the band
         st = None if state_in is None else state_in.numpy().reshape(3, self.Wp, self.D).astype(np.int64)
         out = np.zeros((3, self.Wp, self.D), np.int64)
-        for t, (path, sj, enter) in enumerate(((1, dj, j1), (2, 0, 0), (3, -dj, jl))):
-            pos = (np.arange(self.Wp) + sj * (done - 1 if done else 0)) % self.Wp  # position on the row before the band
-            a = np.zeros((self.Wp, self.D), np.int64) if st is None else st[t]
-            for i in rows:
-                if i == i1:
-                    pos = np.arange(self.Wp)   # first line of the pass: L = C, nothing added (a step from a = 0)
-                else:
-                    pos = pos + sj
-                    wrapped = (pos < 0) | (pos >= self.Wp)
-                    pos = np.where(wrapped, enter, pos)
-                    a[wrapped] = P2
-                q, a = _step(a, self.C[i, pos])
-                self.Q[4 * p + path, i, pos] = q
-            out[t] = a
+        band = (self.row0, self.row1)
+        srow, scol = Sweep(2 * p, self.Hp, self.Wp, self.roi, band), Sweep(2 * p + 1, self.Hp, self.Wp, self.roi, band)
+        if not srow.empty:
+            ex = run_sweep(self.C, srow, self.V[2 * p], None if st is None else st[0][: srow.t1 - srow.t0])
+            out[0][: len(ex)] = ex
+        if not scol.empty:
+            n = scol.n1 - scol.n0
+            a, r = run_sweep(self.C, scol, self.V[2 * p + 1], None if st is None else (st[1][:n], st[2][:n]))
+            out[1][:n], out[2][:n] = a, r
         return torch.from_numpy(out.astype(np.uint8).reshape(-1)) if want_out else None
 
     def finish(self):
         lo, hi = self._crop_rows()
         if hi <= lo:
             return torch.zeros((0, self.W), dtype=torch.int16)
-        S = 8 * self.C[lo:hi] + self.Q[:, lo:hi].sum(axis=0)
+        S = 8 * self.C[lo:hi] + self.V[:, lo:hi].sum(axis=0)
         disp = np.zeros((hi - lo, self.W), np.int64)
         for jj in range(self.W):
             j = jj + self.D
