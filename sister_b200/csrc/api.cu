@@ -25,7 +25,7 @@ struct Slot {
     unsigned long long *d_census = nullptr;
     int16_t *d_wtaL = nullptr, *d_wtaR = nullptr, *d_medL = nullptr, *d_medR = nullptr, *d_lr = nullptr;
     uint8_t *d_masks = nullptr, *d_fused = nullptr;
-    uint8_t *d_paths = nullptr; // 8 one-byte path volumes (sgm.cu)
+    SgmScratch sgm;             // four one-byte pair volumes + the sweeps' mailbox (sgm.cu)
     uint16_t *d_sum = nullptr;  // aggregated volume, allocated only while the test taps are enabled
     int16_t *d_raw = nullptr;
     uint16_t *d_out = nullptr, *h_out = nullptr;
@@ -157,7 +157,7 @@ int run_pipeline(sister_ctx *ctx, Slot &s, const uint8_t *const in_views[5], int
         launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused, s.d_status, s.st, ctx->lc);
         end_stage(ctx, s);
         begin_stage(ctx, s, SISTER_STAGE_AGGREGATE);
-        launch_sgm(s.d_fused, d, ctx->full_frame || ctx->taps, s.d_paths, ctx->taps ? s.d_sum : nullptr, s.d_raw + (size_t)mode * d.px,
+        launch_sgm(s.d_fused, d, ctx->full_frame || ctx->taps, s.sgm, ctx->taps ? s.d_sum : nullptr, s.d_raw + (size_t)mode * d.px,
                    out_dev ? out_dev[mode] : nullptr, s.d_status, s.st, ctx->lc);
         end_stage(ctx, s);
     }
@@ -176,7 +176,7 @@ void free_slot(Slot &s)
     if (s.st) cudaStreamSynchronize(s.st);
     cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_oriented); cudaFree(s.d_census);
     cudaFree(s.d_wtaL); cudaFree(s.d_wtaR); cudaFree(s.d_medL); cudaFree(s.d_medR); cudaFree(s.d_lr);
-    cudaFree(s.d_masks); cudaFree(s.d_fused); cudaFree(s.d_paths); cudaFree(s.d_sum); cudaFree(s.d_raw); cudaFree(s.d_out);
+    cudaFree(s.d_masks); cudaFree(s.d_fused); cudaFree(s.sgm.vols); cudaFree(s.sgm.mailbox); cudaFree(s.d_sum); cudaFree(s.d_raw); cudaFree(s.d_out);
     cudaFreeHost(s.h_out); cudaFree(s.d_status); cudaFreeHost(s.h_status);
     for (auto e : s.ev_b) cudaEventDestroy(e);
     for (auto e : s.ev_e) cudaEventDestroy(e);
@@ -259,7 +259,9 @@ int sister_create(sister_ctx **out, int device, int max_w, int max_h, int max_di
         A((void **)&s.d_oriented, 8 * px); A((void **)&s.d_census, 8 * px * 8);
         A((void **)&s.d_wtaL, 4 * px * 2); A((void **)&s.d_wtaR, 4 * px * 2);
         A((void **)&s.d_medL, 4 * px * 2); A((void **)&s.d_medR, 4 * px * 2); A((void **)&s.d_lr, 4 * px * 2);
-        A((void **)&s.d_masks, 4 * px); A((void **)&s.d_fused, cells); A((void **)&s.d_paths, 8 * cells);
+        A((void **)&s.d_masks, 4 * px); A((void **)&s.d_fused, cells); A((void **)&s.sgm.vols, 4 * cells);
+        s.sgm.mailbox_bytes = sgm_mailbox_bytes(max_w, max_h, max_disp);
+        A((void **)&s.sgm.mailbox, s.sgm.mailbox_bytes);
         A((void **)&s.d_raw, 3 * px * 2); A((void **)&s.d_out, 3 * wh * 2); H((void **)&s.h_out, 3 * wh * 2);
         A((void **)&s.d_status, sizeof(int)); H((void **)&s.h_status, sizeof(int));
         if (e != cudaSuccess) { rc = fail_cuda(nullptr, e, "alloc"); return bail(rc); }
@@ -405,8 +407,13 @@ int sister_submit_device(sister_ctx *ctx, int slot, const uint8_t *const views_d
 
 size_t sister_band_state_bytes(int w, int h, int disp_count)
 {
-    (void)h;
-    return (size_t)3 * (size_t)(w + 2 * disp_count) * (size_t)disp_count;
+    if (w <= 0 || h <= 0 || disp_count <= 0 || disp_count % 8 != 0 || disp_count > 512) return 0;
+    Dims d;
+    d.W = w; d.H = h; d.D = disp_count; d.Wp = w + 2 * disp_count; d.Hp = h + 2 * disp_count;
+    d.px = (long long)d.Wp * d.Hp;
+    d.cells = d.px * disp_count;
+    set_cell_order(d);
+    return sgm_band_state_bytes(d);
 }
 
 int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h, int channels, int disp_count, int mode,
@@ -435,7 +442,6 @@ int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev
     launch_match_wta(s.d_census, d, vm, s.d_wtaL, s.d_wtaR, s.st, ctx->lc);
     launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, vm, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.st, ctx->lc);
     launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused, s.d_status, s.st, ctx->lc, band_row0, band_row1);
-    launch_sgm_band(0, s.d_fused, d, band_row0, band_row1, nullptr, nullptr, s.d_paths, nullptr, nullptr, s.st, ctx->lc);
     SCK(cudaGetLastError());
     SCK(take_launch_error(ctx));
     s.dims = d;
@@ -458,7 +464,7 @@ int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *sta
     const bool last_of_pass = pass == 0 ? s.band_r1 == s.dims.Hp : s.band_r0 == 0;
     if (!first_of_pass && !state_in_dev) { ctx->err = "state_in_dev is NULL but the band is not the first of this pass"; return SISTER_E_ARG; }
     if (!last_of_pass && !state_out_dev) { ctx->err = "state_out_dev is NULL but the band is not the last of this pass"; return SISTER_E_ARG; }
-    launch_sgm_band(1 + pass, s.d_fused, s.dims, s.band_r0, s.band_r1, state_in_dev, state_out_dev, s.d_paths, nullptr, nullptr, s.st, ctx->lc);
+    launch_sgm_band(1 + pass, s.d_fused, s.dims, s.band_r0, s.band_r1, state_in_dev, state_out_dev, s.sgm, nullptr, nullptr, s.d_status, s.st, ctx->lc);
     SCK(cudaGetLastError());
     SCK(take_launch_error(ctx));
     return SISTER_OK;
@@ -471,7 +477,7 @@ int sister_band_finish(sister_ctx *ctx, int slot, uint16_t *out_dev)
     Slot &s = ctx->slots[slot];
     if (!out_dev || s.band_r1 <= s.band_r0) { ctx->err = "sister_band_submit first; out_dev must not be null"; return SISTER_E_ARG; }
     SCK(cudaSetDevice(ctx->device));
-    launch_sgm_band(3, s.d_fused, s.dims, s.band_r0, s.band_r1, nullptr, nullptr, s.d_paths, nullptr, out_dev, s.st, ctx->lc);
+    launch_sgm_band(3, s.d_fused, s.dims, s.band_r0, s.band_r1, nullptr, nullptr, s.sgm, nullptr, out_dev, s.d_status, s.st, ctx->lc);
     SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
     SCK(cudaGetLastError());
     s.band_r0 = s.band_r1 = 0; // sister_sync(slot) completes the band and checks the status word
@@ -713,7 +719,7 @@ int sister_stereo(sister_ctx *ctx, const uint8_t *center, const uint8_t *side, i
     launch_fuse(s.d_census, s.d_masks, d, 0x1u, s.d_fused, s.d_status, s.st, ctx->lc);
     // SGM (hpp:135) + WTA-left (hpp:137) in the final sweep; the aggregated volume is kept for WTA-right (hpp:138)
     ctx->lc.cur_stage = SISTER_STAGE_AGGREGATE;
-    launch_sgm(s.d_fused, d, true, s.d_paths, s.d_sum, s.d_wtaL, nullptr, s.d_status, s.st, ctx->lc);
+    launch_sgm(s.d_fused, d, true, s.sgm, s.d_sum, s.d_wtaL, nullptr, s.d_status, s.st, ctx->lc);
     launch_wta_right_sum(s.d_sum, d, s.d_wtaR, s.st, ctx->lc);
     // median on both maps (hpp:139-140), LRC (hpp:143)
     ctx->lc.cur_stage = SISTER_STAGE_MASK;
@@ -762,7 +768,7 @@ int sister_test_sgm(sister_ctx *ctx, const uint8_t *fused, int w, int h, int dis
     SCK(cudaMemsetAsync(s.d_status, 0, sizeof(int), s.st));
     if (!s.d_sum) SCK(cudaMalloc((void **)&s.d_sum, (size_t)ctx->cells_max * 2));
     ctx->lc.cur_stage = SISTER_STAGE_AGGREGATE;
-    launch_sgm(s.d_fused, d, true, s.d_paths, s.d_sum, s.d_raw, nullptr, s.d_status, s.st, ctx->lc);
+    launch_sgm(s.d_fused, d, true, s.sgm, s.d_sum, s.d_raw, nullptr, s.d_status, s.st, ctx->lc);
     SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
     SCK(cudaGetLastError());
     SCK(cudaStreamSynchronize(s.st));

@@ -56,23 +56,35 @@ void launch_fuse(const unsigned long long *census, const uint8_t *masks, const D
                  int *status, cudaStream_t st, LaunchCounter &lc, int row_lo = 0, int row_hi = -1);
 
 // ---- sgm.cu ----
-// 8-path SGM (sgm.cpp:26-455) on the uint8 fused volume: 8 one-byte path volumes (qvol, 8 * cells bytes), then
-// S = nC * C + sum of the path bytes, the final WTA-left (hpp:283) and convertTo/crop/*255 (hpp:111-118) in one sweep.
+// Aggregation scratch of one slot: the four pair volumes (4 * cells bytes) and the mailbox through which the blocks of a
+// sweep hand the rider states on (sgm_mailbox_bytes), with the epoch of its tags.
+struct SgmScratch {
+    uint8_t *vols = nullptr;
+    uint8_t *mailbox = nullptr;
+    size_t mailbox_bytes = 0;
+    unsigned epoch = 0;
+    unsigned long long geo_key = 0;
+};
+// mailbox size that serves every rig a context of this capacity accepts
+size_t sgm_mailbox_bytes(int max_w, int max_h, int max_d);
+// 8-path SGM (sgm.cpp:26-455) on the uint8 fused volume: four two-path sweeps write four one-byte pair volumes, then
+// S = nC * C + sum of the pair bytes, the final WTA-left (hpp:283) and convertTo/crop/*255 (hpp:111-118) in one sweep.
 // sum (uint16 [Hp][Wp][D]) is written only when non-null (test tap); raw_disp / out may be null.
-// full_frame = false aggregates for the crop Rect(D, D, W, H) only (all the caller ever sees, hpp:116-118): chains that
-// never reach it are skipped, the others stop once they have left it, path bytes exist only inside it. raw_disp and sum
-// are then written inside the crop only.
-void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, uint8_t *qvol, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
+// full_frame = false aggregates for the crop Rect(D, D, W, H) only (all the caller ever sees, hpp:116-118): rows and
+// columns behind it are not run, those in front of it run only the diagonal path that will enter it, bytes exist only
+// inside it. raw_disp and sum are then written inside the crop only.
+void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, SgmScratch &sc, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
                 int *status, cudaStream_t st, LaunchCounter &lc);
 
 // WTARight_SSE on the aggregated volume (hpp:138): int16 map Hp x Wp
 void launch_wta_right_sum(const uint16_t *sum, const Dims &d, int16_t *outR, cudaStream_t st, LaunchCounter &lc);
 
 // One row band [band_r0, band_r1) of the padded frame (a large frame split over several GPUs),
-// crop-only aggregation. what: 0 = the band's row chains, 1 / 2 = the column and diagonal chains of pass 0 / pass 1
-// continued from state_in (the neighbouring band's state_out; null on the first band of the pass) and leaving their
-// state in state_out (null on the last), 3 = final sum / WTA / encode of the band's rows. State: 3 * Wp * D bytes.
+// crop-only aggregation. what: 1 / 2 = the two sweeps of pass 0 / pass 1 inside the band, continued from state_in (the
+// neighbouring band's state_out; null on the first band of the pass) and leaving their state in state_out (null on the
+// last), 3 = final sum / WTA / encode of the band's rows. State: sgm_band_state_bytes.
+size_t sgm_band_state_bytes(const Dims &d);
 void launch_sgm_band(int what, const uint8_t *fused, const Dims &d, int band_r0, int band_r1, const uint8_t *state_in, uint8_t *state_out,
-                     uint8_t *qvol, int16_t *raw_disp, uint16_t *out, cudaStream_t st, LaunchCounter &lc);
+                     SgmScratch &sc, int16_t *raw_disp, uint16_t *out, int *status, cudaStream_t st, LaunchCounter &lc);
 
 } // namespace sister
