@@ -21,4 +21,4 @@ with sister_b200.Engine(W, H, D, n_slots=1) as eng:
         if it >= 2:
             for k, v in eng.stage_ms(0).items():
                 acc[k].append(v)
-    print(os.environ.get("SISTER_DEBUG_PATH_KINDS", "7"), {k: round(statistics.median(v), 4) for k, v in acc.items()})
+    print("nw", os.environ.get("SISTER_DEBUG_SWEEP_NW", "auto"), {k: round(statistics.median(v), 4) for k, v in acc.items()})

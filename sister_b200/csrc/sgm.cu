@@ -44,7 +44,9 @@
 
 namespace sister {
 
-constexpr int kSweepWarpsMax = 8;  // compute warps per block (+ 1 mailbox warp)
+// compute warps per block (+ 1 mailbox warp): up to 18 while a lane holds few registers of state, fewer for the long
+// disparity ranges, whose state needs the registers a smaller block leaves per thread
+constexpr int sweep_warps_max(int NR) { return NR <= 8 ? 18 : NR <= 12 ? 12 : 8; }
 constexpr int kSweepWarpsMin = 6;  // the mailbox allocation of a context is sized for this many (sgm_mailbox_bytes)
 constexpr int kRing = 8;           // cost ring slots per warp
 constexpr int kSpinLimit = 1 << 21;
@@ -427,13 +429,8 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
     }
 }
 
-// resident blocks per SM the register allocation aims at: three for the shapes whose lanes are exactly full up to D = 256
-// (72 registers), fewer for the partial-lane variants (their padding masks cost registers) and the long disparity ranges
-#ifndef SISTER_SWEEP_MINB
-#define SISTER_SWEEP_MINB(NR, FULL) ((FULL) ? ((NR) <= 8 ? 3 : (NR) <= 12 ? 2 : 1) : ((NR) <= 8 ? 2 : 1))
-#endif
 template <int NR, int LPC, bool FULL, bool IL>
-__global__ void __launch_bounds__((kSweepWarpsMax + 1) * 32, SISTER_SWEEP_MINB(NR, FULL))
+__global__ void __launch_bounds__((sweep_warps_max(NR) + 1) * 32)
     k_sgm_sweeps(const uint8_t *__restrict__ fused, Dims d, SweepPlan pl, uint8_t *__restrict__ vols, uint8_t *__restrict__ mailbox, int *__restrict__ status, unsigned one)
 {
     constexpr int CPW = 32 / LPC;
@@ -701,20 +698,31 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
     constexpr int CPW = 32 / LPC;
     const void *kernel = (const void *)k_sgm_sweeps<NR, LPC, FULL, IL>;
     auto smem_for = [&](int nw) { return (size_t)2 * (nw * CPW + 1) * NR * LPC * 4 + (size_t)nw * kRing * CPW * 2 * NR * LPC; };
-    if (smem_for(kSweepWarpsMax) > 48 * 1024) lc.fail(optin_dynamic_smem(kernel, smem_for(kSweepWarpsMax)));
-    // compute warps per block: the most for which the whole pipeline is resident at once (a block that has to wait for a
-    // slot starts its sweep late, which costs up to a whole sweep of time, not just its own share)
+    constexpr int kWarpsMax = sweep_warps_max(NR);
+    if (smem_for(kWarpsMax) > 48 * 1024) lc.fail(optin_dynamic_smem(kernel, smem_for(kWarpsMax)));
+    // Compute warps per block. The blocks of a sweep are a pipeline: it runs at the pace of its slowest block, and a block's
+    // pace is set by how many warps share its SM's issue slots. So the choice is the one that spreads the warps most evenly
+    // over the SMs -- the fewest compute warps on the busiest SM, blocks being dealt round-robin -- among those for which the
+    // whole pipeline is resident at once (a block that has to wait for a slot starts its sweep late, which costs up to a
+    // whole sweep of time, not just its own share); ties go to the larger block (fewer hand-overs through global memory).
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     SweepPlan pl;
-    int nw = kSweepWarpsMax;
-    for (int cand = kSweepWarpsMax; cand >= kSweepWarpsMin; cand--) {
+    int nw = kSweepWarpsMin;
+    long long best = -1;
+    for (int cand = kWarpsMax; cand >= kSweepWarpsMin; cand--) {
         plan_sweeps(d, roi, b0, b1, mask, cand, pl);
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (cand + 1) * 32, smem_for(cand)) != cudaSuccess) per_sm = 1;
-        if (pl.total_blocks <= per_sm * n_sm) { nw = cand; break; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (cand + 1) * 32, smem_for(cand)) != cudaSuccess) per_sm = 0;
+        const long long on_busiest = (pl.total_blocks + n_sm - 1) / n_sm;
+        // not resident at once: the sweeps run in waves, every wave a whole sweep long
+        const long long cost = on_busiest <= per_sm ? on_busiest * cand : (1LL << 40) + on_busiest * cand;
+        if (best < 0 || cost < best) { best = cost; nw = cand; }
     }
+#ifdef SISTER_DEBUG_HOOKS
+    if (const char *e = getenv("SISTER_DEBUG_SWEEP_NW")) nw = std::min(std::max(atoi(e), kSweepWarpsMin), kWarpsMax); // measurement aid
+#endif
     plan_sweeps(d, roi, b0, b1, mask, nw, pl);
     if (pl.total_blocks == 0) return;
     const long long eb = entry_bytes(d);
