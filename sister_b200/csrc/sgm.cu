@@ -136,22 +136,24 @@ template <int NR> __device__ __forceinline__ void state_to_words(const uint32_t 
 #pragma unroll
     for (int k = 0; k < NR / 2; k++) w[k] = ((a[2 * k + 1] * 256u + a[2 * k]) & 0x7F7F7F7Fu) | tag; // pads (disparities >= D) are dropped
 }
-template <int NR, int LPC, bool FULL> __device__ __forceinline__ void words_to_state(const uint32_t (&w)[NR / 2], const LaneInfo<NR, LPC, FULL> &li, uint32_t (&a)[NR])
+// `off` (0 or the phase offset of the exchange ring, below) is added to the disparities' halves before the padding halves
+// are set to their constant
+template <int NR, int LPC, bool FULL> __device__ __forceinline__ void words_to_state(const uint32_t (&w)[NR / 2], const LaneInfo<NR, LPC, FULL> &li, uint32_t (&a)[NR], uint32_t off = 0u)
 {
 #pragma unroll
     for (int k = 0; k < NR / 2; k++) {
         const uint32_t x = w[k] & 0x7F7F7F7Fu;
-        a[2 * k + 1] = li.padded(__byte_perm(x, 0u, 0x4341), 2 * k + 1);
-        a[2 * k] = li.padded(x & 0x00FF00FFu, 2 * k);
+        a[2 * k + 1] = li.padded(__byte_perm(x, 0u, 0x4341) + off, 2 * k + 1);
+        a[2 * k] = li.padded((x & 0x00FF00FFu) + off, 2 * k);
     }
 }
 // plain (untagged) entry in global memory: a band state
-template <int NR, int LPC, bool FULL> __device__ __forceinline__ void entry_load(const uint8_t *entry, const LaneInfo<NR, LPC, FULL> &li, uint32_t (&a)[NR])
+template <int NR, int LPC, bool FULL> __device__ __forceinline__ void entry_load(const uint8_t *entry, const LaneInfo<NR, LPC, FULL> &li, uint32_t (&a)[NR], uint32_t off = 0u)
 {
     uint32_t w[NR / 2];
 #pragma unroll
     for (int k = 0; k < NR / 2; k++) w[k] = __ldg(reinterpret_cast<const uint32_t *>(entry) + k * LPC + li.sl);
-    words_to_state<NR, LPC, FULL>(w, li, a);
+    words_to_state<NR, LPC, FULL>(w, li, a, off);
 }
 template <int NR, int LPC, bool FULL> __device__ __forceinline__ void entry_store(uint8_t *entry, const LaneInfo<NR, LPC, FULL> &li, const uint32_t (&a)[NR])
 {
@@ -161,10 +163,15 @@ template <int NR, int LPC, bool FULL> __device__ __forceinline__ void entry_stor
     for (int k = 0; k < NR / 2; k++) reinterpret_cast<uint32_t *>(entry)[k * LPC + li.sl] = w[k];
 }
 
-// One step of the rider: the state arrives as `a` only (from the neighbouring chain), b and the end neighbours are formed
-// here, and the new state leaves as `a` only.
+// One step of the rider. Its state travels between chains in the OFFSET DOMAIN: every 16-bit half carries + off, off = 0x100
+// on odd laps of the exchange ring, 0 on even ones -- bit 8 of a half is the entry's phase tag (states are <= P2 + P1 < 256),
+// so every 32-bit word of an entry says by itself whether it belongs to the lap the reader expects. The offset costs
+// nothing: it rides through min / + unchanged, cancels in the normalisation (L' - min L') and is replaced by the writer's
+// own phase in the constants of that same instruction. The state arrives as `a` only, b and the end neighbours are formed
+// here, and the new state leaves as `a` only; q comes out carrying the reader's offset (the caller subtracts it).
 template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ void rider_step(const uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo<NR, LPC, FULL> &li, uint32_t (&q)[NR], uint32_t (&out)[NR])
+__device__ __forceinline__ void rider_step(const uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo<NR, LPC, FULL> &li, uint32_t off_out16, uint32_t clamp2,
+                                           uint32_t (&q)[NR], uint32_t (&out)[NR])
 {
     uint32_t b[NR], left, right, L[NR];
 #pragma unroll
@@ -176,18 +183,62 @@ __device__ __forceinline__ void rider_step(const uint32_t (&a)[NR], const uint32
         L[k] = li.padded(q[k] + c[k], k);
     }
     const uint32_t mm = chain_min2<LPC>(lane_min<NR>(L));
-    const uint32_t neg2 = __byte_perm(0u - mm, 0u, 0x1010);
+    const uint32_t neg2 = __byte_perm(off_out16 - mm, 0u, 0x1010); // (off_out - min) mod 2^16 in both halves
 #pragma unroll
-    for (int k = 0; k < NR; k++) out[k] = li.padded(__viaddmin_s16x2(L[k], neg2, kP2x2), k);
+    for (int k = 0; k < NR; k++) out[k] = li.padded(__viaddmin_s16x2(L[k], neg2, clamp2), k);
+}
+
+constexpr uint32_t kPhase2 = 0x01000100u; // the phase tag of both halves of a word
+constexpr int kXR = 4;                     // exchange ring: entries per chain boundary (= steps per trip of the step loop)
+
+// the tag bits of register k that hold a disparity (padding halves always read 0x3FFF)
+template <int NR, int LPC, bool FULL> __device__ __forceinline__ uint32_t phase_bits(const LaneInfo<NR, LPC, FULL> &li, int k)
+{
+    if constexpr (FULL) return kPhase2;
+    else return kPhase2 & ~li.pad[k];
+}
+
+__device__ __forceinline__ uint32_t lds_volatile(unsigned a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(unsigned a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
+
+// Wait until entry `entry_s` carries the expected phase in every word, and read it. Returns false after kSpinLimit polls
+// (a broken pipeline must never hang the device: the caller reports it and stops waiting).
+template <int NR, int LPC, bool FULL>
+__device__ __forceinline__ bool xch_wait_read(unsigned entry_s, const LaneInfo<NR, LPC, FULL> &li, uint32_t expw, bool on, bool &broken, uint32_t (&a)[NR])
+{
+    int spins = 0;
+    for (;;) {
+        xch_read<NR, LPC>(entry_s, li.sl, a);
+        uint32_t bad = 0u;
+#pragma unroll
+        for (int k = 0; k < NR; k++) bad |= (a[k] ^ expw) & phase_bits<NR, LPC, FULL>(li, k);
+        if (!__any_sync(kFull, on && bad != 0u) || broken) return true;
+        if (++spins > kSpinLimit) { broken = true; return false; }
+    }
+}
+// wait until the reader behind boundary ring `done_s` has read what slot (s mod kXR) held a lap ago
+__device__ __forceinline__ bool xch_wait_free(unsigned done_s, int s, bool &broken)
+{
+    int spins = 0;
+    while ((int)lds_volatile(done_s) < s - (kXR - 2) && !broken)
+        if (++spins > kSpinLimit) { broken = true; return false; }
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------- the sweep kernel
 
 // MODE 0: carrier + rider; 1: rider only (chains in front of the region); 2: the warp that holds the first line of a row
-// sweep (carrier = the literal first-line arithmetic, rider restarts from the zero state at every step)
+// sweep (carrier = the literal first-line arithmetic, rider restarts from the zero state at every step, nothing is read)
+//
+// Hand-over inside a block: boundary e (0 .. chains of the block) is a ring of kXR entries in shared memory; the chain in
+// slot e - 1 writes the state it left after step s into entry s mod kXR with phase (s / kXR) & 1, the chain in slot e polls
+// that entry's phase at step s + 1. No barrier, no fence: warps run free, each as far behind its predecessor as the
+// hand-over takes. A writer must not lap its reader: a warp publishes how many steps' inputs it has read (done[warp]) and the
+// warp in front checks it before every write (chains of one warp are in lock step and need no check).
 template <int NR, int LPC, bool FULL, bool IL, int MODE>
 __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, uint8_t *__restrict__ vol, const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, int D,
-                                           int n, bool alive, bool car, int cl, unsigned ring_s, unsigned x_s, int x_stride, int lane, int n_sync)
+                                           int n, bool alive, bool car, int cl, unsigned ring_s, unsigned x_s, unsigned my_done_s, unsigned cons_done_s, int lane,
+                                           int n_sync, int *__restrict__ status)
 {
     constexpr int CPW = 32 / LPC;
     constexpr int DS = 2 * NR * LPC;          // bytes of a cell in a ring slot (>= D), of a mailbox / band entry
@@ -196,9 +247,11 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
     constexpr int SS = CPW * DS;              // bytes per ring slot
     constexpr int R = kRing, A = R - 1, U = R / 2;
     constexpr int EX = NR * LPC * 4;          // bytes of an exchange entry
+    static_assert(U == kXR, "a trip of the step loop is one lap of the exchange ring");
     const int T = g.t1 - g.t0;
     const int sub = lane / LPC;
     const int valid_bytes = li.valid_bytes(D);
+    const int ts_lo = g.ts0 - g.t0, ts_n = g.ts1 - g.ts0; // steps (relative to the first) whose cells are stored
     // ---- cost ring: chunk gch = lane + 32 m of a warp step belongs to the cell of sub-chain gch / chunks-per-cell
     const int cpc = FULL ? DS / CB : D / CB;
     const uint8_t *cp_src[NCP];
@@ -215,8 +268,8 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
         cp_dst[m] = ring_s + cs * DS + (gch - cs * cpc) * CB;
     }
     const long long step_bytes = (long long)g.st8 * 8;
-    auto copy_step = [&](const int s, const unsigned slot_off) { // the cells of step s (where the copy cursors stand) -> the slot, move on
-        if (s < T) {
+    auto copy_step = [&](const bool go, const unsigned slot_off) { // the cells where the copy cursors stand -> the slot, move on
+        if (go) {
 #pragma unroll
             for (int m = 0; m < NCP; m++) {
                 if (cp_on[m]) {
@@ -229,11 +282,12 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
         cp_async_commit();
     };
 #pragma unroll
-    for (int s = 0; s < A; s++) copy_step(s, s * SS);
+    for (int s = 0; s < A; s++) copy_step(s < T, s * SS);
     const unsigned rd_lane = ring_s + sub * DS + li.template cell_offset<IL>();
     unsigned half = 0, other = U * SS;
+    uint32_t phase = 0u; // kPhase2 on odd trips
     auto wr_off = [&](const int u) { return u == 0 ? other + (U - 1) * SS : half + (u - 1) * SS; };
-    auto next_trip = [&]() { const unsigned t = half; half = other; other = t; };
+    auto next_trip = [&]() { const unsigned t = half; half = other; other = t; phase ^= kPhase2; };
     // ---- state
     ChainState<NR> cs;
     uint32_t mm = 0; // MODE 2: minimum of the truncated first-line state
@@ -241,20 +295,32 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
     uint32_t rider_out[NR];
 #pragma unroll
     for (int k = 0; k < NR; k++) rider_out[k] = 0u;
-    const unsigned x_in = x_s + (unsigned)cl * EX, x_out = x_in + EX; // + parity * x_stride
+    const unsigned x_in = x_s + (unsigned)cl * (kXR * EX), x_out = x_in + kXR * EX; // + entry * EX
     const bool frame_start = g.t0 == 0;
     const long long band_chain = (long long)(n - g.n0) * DS, band_riders = (long long)(g.n1 - g.n0) * DS;
+    {   // shared memory keeps what the previous kernel left: every entry of the ring this chain writes starts in phase 1, the
+        // lap before the first, so that no reader takes stale bytes for the state it is waiting for
+        uint32_t a[NR];
+#pragma unroll
+        for (int k = 0; k < NR; k++) a[k] = kPhase2;
+#pragma unroll
+        for (int e = 0; e < kXR; e++) xch_write<NR, LPC>(x_out + e * EX, li.sl, a);
+    }
     if (!g.row && g.band_in) { // a column sweep continued from the band before: [carrier states | rider states] per chain
         uint32_t a[NR];
         entry_load<NR, LPC, FULL>(g.band_in + band_chain, li, a);
         chain_resume<NR, LPC, FULL>(cs, a, li);
-        entry_load<NR, LPC, FULL>(g.band_in + band_riders + band_chain, li, rider_out);
-        xch_write<NR, LPC>(x_out, li.sl, rider_out); // what this chain left after the step before the band: parity 0 = first step of the band
+        // what this chain left after the step before the band: entry kXR - 1 of the lap before the first (phase 1)
+        entry_load<NR, LPC, FULL>(g.band_in + band_riders + band_chain, li, a, kPhase2);
+        xch_write<NR, LPC>(x_out + (kXR - 1) * EX, li.sl, a);
     }
     uint8_t *dst = vol + (long long)my_off8 * 8 + li.template cell_offset<IL>();
-    block_sync(n_sync); // the exchange entries of the first step (helper: predecessor block / constants; above: band states) are in place
-    auto step = [&](const int s, const int u, auto first_tag) {
-        constexpr bool FIRST = decltype(first_tag)::value; // a trip that may contain the frame's step 0
+    block_sync(n_sync); // done[] is zero, the entries of the first step (band states) are in place
+    bool broken = false;
+    // GEN: the general step (first trip, trips that straddle an edge of the stored range, tail); otherwise STORE says whether
+    // the whole trip lies inside the stored range, and nothing is tested
+    auto step = [&](const int s, const int u, auto gen_tag, auto store_tag) {
+        constexpr bool GEN = decltype(gen_tag)::value, STORE = decltype(store_tag)::value;
         uint32_t c[NR], q1[NR];
         {
             cp_async_wait<A - 1>();
@@ -263,108 +329,111 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
             ring_read<NR, LPC, FULL, IL>(rd_lane + half + u * SS, valid_bytes, w);
             // a first-line cell reads the invalid cost 255 (census.cpp:76) as 0 (sgm.cpp:109,123,146); fused volumes never
             // hold 255 (match.cu), the raw two-view volume of sister_stereo does
-            if (MODE == 2 || (FIRST && !g.row && frame_start && s == 0)) {
+            if (MODE == 2 || (GEN && !g.row && frame_start && s == 0)) {
 #pragma unroll
                 for (int k = 0; k < NR / 2; k++) w[k] &= ~__vcmpeq4(w[k], 0xFFFFFFFFu);
             }
             unpack_cost<NR, IL>(w, c);
         }
-        copy_step(s + A, wr_off(u));
-        const unsigned par_out = (u & 1) ? 0u : (unsigned)x_stride;
+        copy_step(!GEN || s + A < T, wr_off(u));
         // ---- rider
-        uint32_t ra[NR];
-        if constexpr (MODE == 2) {
+        uint32_t ra[NR], off_in = 0u;
+        if (MODE == 2 || (GEN && frame_start && s == 0)) {
+            // first line: zero state; row sweep at its first column: the predecessor is off the image
+            const uint32_t v = (MODE != 2 && g.row) ? kP2x2 : 0u;
 #pragma unroll
-            for (int k = 0; k < NR; k++) ra[k] = li.padded(0u, k);
+            for (int k = 0; k < NR; k++) ra[k] = li.padded(v, k);
         } else {
-            xch_read<NR, LPC>(x_in + ((u & 1) ? (unsigned)x_stride : 0u), li.sl, ra);
-            if (FIRST && frame_start && s == 0) { // row sweep: the predecessor column is off the image; column sweep: first line
-                const uint32_t v = g.row ? kP2x2 : 0u;
-#pragma unroll
-                for (int k = 0; k < NR; k++) ra[k] = li.padded(v, k);
-            }
+            off_in = u == 0 ? phase ^ kPhase2 : phase; // the state after step s - 1: previous entry, previous lap for u == 0
+            if (!xch_wait_read<NR, LPC, FULL>(x_in + ((u + kXR - 1) % kXR) * EX, li, off_in, true, broken, ra) && lane == 0) atomicOr(status, kStatusSpinTimeout);
+            if (lane == 0) sts32(my_done_s, (uint32_t)(s + 1));
         }
-        rider_step<NR, LPC, FULL>(ra, c, li, q1, rider_out);
-        xch_write<NR, LPC>(x_out + par_out, li.sl, rider_out);
+        rider_step<NR, LPC, FULL>(ra, c, li, phase >> 16, kP2x2 + phase, q1, rider_out);
+        if (cons_done_s != 0u && !xch_wait_free(cons_done_s, s, broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
+        xch_write<NR, LPC>(x_out + u * EX, li.sl, rider_out);
         // ---- carrier, sum, store
         if constexpr (MODE != 1) {
             uint32_t q0[NR];
             if constexpr (MODE == 2) first_line_step<NR, LPC, FULL>(cs.a, cs.b, mm, c, li, s == 0, q0);
             else chain_step<NR, LPC, FULL>(cs, c, li, q0);
-            if (car && (unsigned)(g.t0 + s - g.ts0) < (unsigned)(g.ts1 - g.ts0)) {
+            if (GEN ? (car && (unsigned)(s - ts_lo) < (unsigned)ts_n) : STORE) {
 #pragma unroll
-                for (int k = 0; k < NR; k++) q0[k] += q1[k];
+                for (int k = 0; k < NR; k++) q0[k] = q0[k] + q1[k] - off_in;
                 store_q<NR, LPC, FULL, IL>(dst, q0, valid_bytes);
             }
             dst += step_bytes;
         }
-        block_sync(n_sync);
     };
+    const bool all_car = __all_sync(kFull, car);
     int s0 = 0;
-    if (U <= T) { // the first trip may hold the frame's step 0
-#pragma unroll
-        for (int u = 0; u < U; u++) step(s0 + u, u, std::true_type{});
-        next_trip();
-        s0 += U;
-    }
 #pragma unroll 1
     while (s0 + U <= T) {
+        const bool inside = s0 >= ts_lo && s0 + U <= ts_lo + ts_n, outside = s0 + U <= ts_lo || s0 >= ts_lo + ts_n;
+        if (s0 > 0 && s0 + U + A <= T && inside && (all_car || MODE == 1)) {
 #pragma unroll
-        for (int u = 0; u < U; u++) step(s0 + u, u, std::false_type{});
+            for (int u = 0; u < U; u++) step(s0 + u, u, std::false_type{}, std::true_type{});
+        } else if (s0 > 0 && s0 + U + A <= T && (outside || MODE == 1)) {
+#pragma unroll
+            for (int u = 0; u < U; u++) step(s0 + u, u, std::false_type{}, std::false_type{});
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) step(s0 + u, u, std::true_type{}, std::false_type{});
+        }
         next_trip();
         s0 += U;
     }
 #pragma unroll
     for (int u = 0; u < U - 1; u++)
-        if (s0 + u < T) step(s0 + u, u, std::true_type{}); // warp-uniform; T < U: this is the first trip
+        if (s0 + u < T) step(s0 + u, u, std::true_type{}, std::false_type{}); // warp-uniform
     cp_async_wait<0>();
     if (!g.row && g.band_out && alive) { // leave the column sweep's states for the next band
+        uint32_t a[NR];
+        const uint32_t last_phase = ((T - 1) / kXR) & 1 ? kPhase2 : 0u;
+#pragma unroll
+        for (int k = 0; k < NR; k++) a[k] = rider_out[k] - last_phase;
         entry_store<NR, LPC, FULL>(g.band_out + band_chain, li, cs.a);
-        entry_store<NR, LPC, FULL>(g.band_out + band_riders + band_chain, li, rider_out);
+        entry_store<NR, LPC, FULL>(g.band_out + band_riders + band_chain, li, a);
     }
 }
 
-// The mailbox warp of a block: lanes [0, LPC) bring the predecessor block's rider state for the NEXT step into exchange
-// entry 0, lanes [LPC, 2 LPC) publish what the block's last chain left after the PREVIOUS step; both meet the compute warps
-// at the step's barrier. Entries are read two steps ahead so that the L2 round trip is off the step's critical path.
+// The import warp of a block: brings the rider states of the predecessor block's last chain (or of the band before, or the
+// constant P2 of the border column) into boundary 0 of the exchange ring, one entry per step, reading the mailbox two
+// entries ahead so that the L2 round trip stays off the consumers' path.
 template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, int b, int ch, int last_e, uint8_t *__restrict__ mailbox, unsigned tagword,
-                                             unsigned x_s, int x_stride, int lane, int n_sync, int *__restrict__ status)
+__device__ __forceinline__ void import_warp(const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, int b, int ch, const uint8_t *__restrict__ mailbox, unsigned tagword,
+                                            unsigned x_s, unsigned done0_s, int lane, int n_sync, int *__restrict__ status)
 {
     constexpr int NH = NR / 2;
     constexpr int EX = NR * LPC * 4;
     constexpr long long EB = 2 * NR * LPC; // bytes of a mailbox / band entry
     const int T = g.t1 - g.t0;
-    const bool imp = lane < LPC, exp = lane >= LPC && lane < 2 * LPC;
-    // where the predecessor's states come from, where the last chain's states go
+    const bool on = lane < LPC;
     const uint8_t *src = nullptr;
     unsigned src_tag = 0u, src_mask = 0u;
     if (b > 0) { src = mailbox + (g.mb_off + (long long)(b - 1) * T) * EB; src_tag = tagword; src_mask = 0x80808080u; }
     else if (g.row && g.band_in) src = g.band_in; // the band before left one state per step, untagged
-    uint8_t *dst = nullptr;
-    unsigned dst_tag = 0u;
-    if (b < g.nblk - 1) { dst = mailbox + (g.mb_off + (long long)b * T) * EB; dst_tag = tagword; }
-    else if (g.row && g.band_out) dst = g.band_out;
     const long long lane_off = (long long)li.sl * 4;
     uint32_t a[NR];
-    // entry 0 at the first step. A column sweep continued from the band before takes the predecessor of the block's first
-    // chain from the band state. With no predecessor at all (column sweep: the border column, rider = P2 for good; row sweep:
-    // the first line, whose warp ignores the entry) the constant goes into both parities once.
-    if (imp) {
-        if (!g.row && g.band_in && b > 0) {
-            const long long pred = (long long)b * ch - 1; // chain before the block's first (column sweeps have no lead)
-            entry_load<NR, LPC, FULL>(g.band_in + ((long long)(g.n1 - g.n0) + pred) * EB, li, a);
-            xch_write<NR, LPC>(x_s, li.sl, a);
-        } else if (!src) {
+    if (on) { // boundary 0 starts in phase 1, the lap before the first (see sweep_warp)
 #pragma unroll
-            for (int k = 0; k < NR; k++) a[k] = li.padded(kP2x2, k);
-            xch_write<NR, LPC>(x_s, li.sl, a);
-            xch_write<NR, LPC>(x_s + x_stride, li.sl, a);
-        }
+        for (int k = 0; k < NR; k++) a[k] = kPhase2;
+#pragma unroll
+        for (int e = 0; e < kXR; e++) xch_write<NR, LPC>(x_s + e * EX, li.sl, a);
     }
+    if (on && !g.row && g.band_in) {
+        // a column sweep continued from the band before: the state the predecessor of the block's first chain left (the
+        // border column has none: P2)
+        if (b > 0) entry_load<NR, LPC, FULL>(g.band_in + ((long long)(g.n1 - g.n0) + (long long)b * ch - 1) * EB, li, a, kPhase2);
+        else {
+#pragma unroll
+            for (int k = 0; k < NR; k++) a[k] = li.padded(kP2x2 + kPhase2, k);
+        }
+        xch_write<NR, LPC>(x_s + (kXR - 1) * EX, li.sl, a);
+    }
+    block_sync(n_sync);
     uint32_t pf0[NH], pf1[NH];
     auto fetch = [&](const int s, uint32_t (&w)[NH]) { // entry s of the source: the predecessor's state after step s
-        if (imp && src && s < T - 1) {
+        if (on && src && s < T - 1) {
             const uint8_t *e = src + (long long)s * EB + lane_off;
 #pragma unroll
             for (int k = 0; k < NH; k++) w[k] = ld_relaxed(e + (long long)k * LPC * 4);
@@ -375,66 +444,79 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
     };
     fetch(0, pf0);
     fetch(1, pf1);
-    block_sync(n_sync);
-    const unsigned x_last = x_s + (unsigned)last_e * EX;
     int spins = 0;
+    bool broken = false;
 #pragma unroll 1
-    for (int s = 0; s < T; s++) {
-        // ---- publish the state the last chain left after step s - 1
-        if (exp && dst && s > 0) {
-            xch_read<NR, LPC>(x_last + ((s & 1) ? x_stride : 0), li.sl, a);
-            uint32_t w[NH];
-            state_to_words<NR>(a, dst_tag, w);
-            uint8_t *e = dst + (long long)(s - 1) * EB + lane_off;
-#pragma unroll
-            for (int k = 0; k < NH; k++) st_relaxed(e + (long long)k * LPC * 4, w[k]);
-        }
-        // ---- deliver the predecessor's state after step s for step s + 1
+    for (int s = 0; s < T - 1; s++) {
         uint32_t w[NH];
+        const uint32_t ph = (s / kXR) & 1 ? kPhase2 : 0u;
 #pragma unroll
         for (int k = 0; k < NH; k++) { w[k] = pf0[k]; pf0[k] = pf1[k]; }
         fetch(s + 2, pf1);
-        if (src && s < T - 1) { // warp-uniform
+        if (src) { // warp-uniform
             for (;;) {
                 uint32_t bad = 0u;
 #pragma unroll
                 for (int k = 0; k < NH; k++) bad |= (w[k] ^ src_tag) & src_mask;
-                if (!__any_sync(kFull, imp && bad != 0u)) break;
+                if (!__any_sync(kFull, on && bad != 0u)) break;
                 if (++spins > kSpinLimit) { // never hang the device: report and carry on with what is there
                     if (lane == 0) atomicOr(status, kStatusSpinTimeout);
                     src_mask = 0u;
                     break;
                 }
-                __nanosleep(32);
-                if (imp) {
+                __nanosleep(20);
+                if (on) {
                     const uint8_t *e = src + (long long)s * EB + lane_off;
 #pragma unroll
                     for (int k = 0; k < NH; k++) w[k] = ld_relaxed(e + (long long)k * LPC * 4);
                 }
             }
-            if (imp) {
-                words_to_state<NR, LPC, FULL>(w, li, a);
-                xch_write<NR, LPC>(x_s + ((s & 1) ? 0 : x_stride), li.sl, a);
-            }
-        }
-        block_sync(n_sync);
-    }
-    if (exp && dst) { // the state after the last step
-        xch_read<NR, LPC>(x_last + ((T & 1) ? x_stride : 0), li.sl, a);
-        uint32_t w[NH];
-        state_to_words<NR>(a, dst_tag, w);
-        uint8_t *e = dst + (long long)(T - 1) * EB + lane_off;
+            words_to_state<NR, LPC, FULL>(w, li, a, ph);
+        } else {
 #pragma unroll
-        for (int k = 0; k < NH; k++) st_relaxed(e + (long long)k * LPC * 4, w[k]);
+            for (int k = 0; k < NR; k++) a[k] = li.padded(kP2x2 + ph, k); // the border column of a column sweep
+        }
+        if (!xch_wait_free(done0_s, s, broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
+        if (on) xch_write<NR, LPC>(x_s + (s % kXR) * EX, li.sl, a);
+    }
+}
+
+// The export warp of a block: publishes the rider states the block's last chain leaves, one mailbox (or band) entry per step.
+template <int NR, int LPC, bool FULL>
+__device__ __forceinline__ void export_warp(const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, uint8_t *__restrict__ dst, unsigned dst_tag, unsigned x_last,
+                                            unsigned my_done_s, int lane, int n_sync, int *__restrict__ status)
+{
+    constexpr int NH = NR / 2;
+    constexpr int EX = NR * LPC * 4;
+    constexpr long long EB = 2 * NR * LPC;
+    const int T = g.t1 - g.t0;
+    const bool on = lane < LPC;
+    block_sync(n_sync);
+    bool broken = false;
+#pragma unroll 1
+    for (int s = 0; s < T; s++) {
+        uint32_t a[NR], w[NH];
+        const uint32_t ph = (s / kXR) & 1 ? kPhase2 : 0u;
+        if (!xch_wait_read<NR, LPC, FULL>(x_last + (s % kXR) * EX, li, ph, on, broken, a) && lane == 0) atomicOr(status, kStatusSpinTimeout);
+        if (lane == 0) sts32(my_done_s, (uint32_t)(s + 2)); // as a reader this warp is at the step after the one it publishes
+#pragma unroll
+        for (int k = 0; k < NR; k++) a[k] -= ph;
+        state_to_words<NR>(a, dst_tag, w);
+        if (on) {
+            uint8_t *e = dst + (long long)s * EB + (long long)li.sl * 4;
+#pragma unroll
+            for (int k = 0; k < NH; k++) st_relaxed(e + (long long)k * LPC * 4, w[k]);
+        }
     }
 }
 
 template <int NR, int LPC, bool FULL, bool IL>
-__global__ void __launch_bounds__((sweep_warps_max(NR) + 1) * 32)
+__global__ void __launch_bounds__((sweep_warps_max(NR) + 2) * 32)
     k_sgm_sweeps(const uint8_t *__restrict__ fused, Dims d, SweepPlan pl, uint8_t *__restrict__ vols, uint8_t *__restrict__ mailbox, int *__restrict__ status, unsigned one)
 {
     constexpr int CPW = 32 / LPC;
     constexpr int EX = NR * LPC * 4;
+    constexpr long long EB = 2 * NR * LPC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // ---- which sweep, which block of it: blocks are dealt round-robin over the sweeps that still have blocks at that
@@ -447,18 +529,33 @@ __global__ void __launch_bounds__((sweep_warps_max(NR) + 1) * 32)
     const int b = pl.lvl_pos[lvl] + rel / pl.lvl_n[lvl];
     const SweepGeo &g = pl.g[s_id];
     const int nw = pl.nw, CH = nw * CPW;
+    const int T = g.t1 - g.t0;
     const int slots_left = g.n1 - g.n0 + g.lead - b * CH; // slots from this block's first to the sweep's last chain
     const int last_e = slots_left < CH ? slots_left : CH;
     const int n_live = (last_e + CPW - 1) / CPW;
-    const int n_sync = (n_live + 1) * 32;
     LaneInfo<NR, LPC, FULL> li;
     li.init(lane, d.D);
     opaque(li.up_mask); opaque(li.dn_mask);
     li.one = one; // a kernel argument: the only 1 neither nvvm nor ptxas can fold (add_fma)
-    const unsigned x_s = (unsigned)__cvta_generic_to_shared(smem_raw);
-    const int x_stride = (CH + 1) * EX;
+    // shared memory: done[nw + 2] words, the exchange rings of CH + 1 boundaries, the warps' cost rings
+    const unsigned done_s = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned x_s = done_s + 128u;
+    const unsigned rings_s = x_s + (unsigned)(CH + 1) * (kXR * EX);
+    // who feeds boundary 0, who drains the last boundary
+    const bool first_line_block = g.row && g.n0 == 0 && b == 0; // its first warp holds the first line and reads nothing
+    const bool has_import = !first_line_block && T > 1;
+    uint8_t *dst = nullptr;
+    unsigned dst_tag = 0u;
+    if (b < g.nblk - 1) { dst = mailbox + (g.mb_off + (long long)b * T) * EB; dst_tag = pl.tagword; }
+    else if (g.row && g.band_out) dst = g.band_out;
+    const int n_sync = (n_live + (has_import ? 1 : 0) + (dst ? 1 : 0)) * 32;
+    if (threadIdx.x < 32) sts32(done_s + 4u * threadIdx.x, 0u); // (nw + 2 <= 20 counters)
     if (warp == nw) {
-        mailbox_warp<NR, LPC, FULL>(li, g, b, CH, last_e, mailbox, pl.tagword, x_s, x_stride, lane, n_sync, status);
+        if (has_import) import_warp<NR, LPC, FULL>(li, g, b, CH, mailbox, pl.tagword, x_s, done_s, lane, n_sync, status);
+        return;
+    }
+    if (warp == nw + 1) {
+        if (dst) export_warp<NR, LPC, FULL>(li, g, dst, dst_tag, x_s + (unsigned)last_e * (kXR * EX), done_s + 4u * (unsigned)nw, lane, n_sync, status);
         return;
     }
     if (warp >= n_live) return;
@@ -469,13 +566,18 @@ __global__ void __launch_bounds__((sweep_warps_max(NR) + 1) * 32)
     const bool alive = u >= g.lead && n < g.n1;
     n = n < g.n0 ? g.n0 : n >= g.n1 ? g.n1 - 1 : n; // dead slots shadow a real chain (their stores are off)
     const bool car = alive && n >= g.car0 && n < g.car1;
-    const unsigned ring_s = x_s + 2u * (unsigned)x_stride + (unsigned)warp * (kRing * CPW * 2 * NR * LPC);
+    const unsigned ring_s = rings_s + (unsigned)warp * (kRing * CPW * 2 * NR * LPC);
     uint8_t *vol = vols + (size_t)g.vol * (size_t)d.cells;
-    const bool first_line_warp = g.row && g.n0 == 0 && b == 0 && warp == 0; // holds chain 0 in its last sub-chain, the others are dead
+    // the reader behind this warp's last boundary: the next warp, or the export warp when the block's last chain is here
+    unsigned cons_done_s = 0u;
+    if (warp + 1 < n_live) cons_done_s = done_s + 4u * (unsigned)(warp + 1);
+    else if (dst) cons_done_s = done_s + 4u * (unsigned)nw;
+    const unsigned my_done_s = done_s + 4u * (unsigned)warp;
+    const bool first_line_warp = first_line_block && warp == 0; // holds chain 0 in its last sub-chain, the others are dead
     const bool any_car = __any_sync(kFull, car);
-    if (first_line_warp) sweep_warp<NR, LPC, FULL, IL, 2>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, x_stride, lane, n_sync);
-    else if (!any_car) sweep_warp<NR, LPC, FULL, IL, 1>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, x_stride, lane, n_sync);
-    else sweep_warp<NR, LPC, FULL, IL, 0>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, x_stride, lane, n_sync);
+    if (first_line_warp) sweep_warp<NR, LPC, FULL, IL, 2>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, my_done_s, cons_done_s, lane, n_sync, status);
+    else if (!any_car) sweep_warp<NR, LPC, FULL, IL, 1>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, my_done_s, cons_done_s, lane, n_sync, status);
+    else sweep_warp<NR, LPC, FULL, IL, 0>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, my_done_s, cons_done_s, lane, n_sync, status);
 }
 
 // ---------------------------------------------------------------------------------------------- final sum + WTA + encode
@@ -697,7 +799,7 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
 {
     constexpr int CPW = 32 / LPC;
     const void *kernel = (const void *)k_sgm_sweeps<NR, LPC, FULL, IL>;
-    auto smem_for = [&](int nw) { return (size_t)2 * (nw * CPW + 1) * NR * LPC * 4 + (size_t)nw * kRing * CPW * 2 * NR * LPC; };
+    auto smem_for = [&](int nw) { return (size_t)128 + (size_t)kXR * (nw * CPW + 1) * NR * LPC * 4 + (size_t)nw * kRing * CPW * 2 * NR * LPC; };
     constexpr int kWarpsMax = sweep_warps_max(NR);
     if (smem_for(kWarpsMax) > 48 * 1024) lc.fail(optin_dynamic_smem(kernel, smem_for(kWarpsMax)));
     // Compute warps per block. The blocks of a sweep are a pipeline: it runs at the pace of its slowest block, and a block's
@@ -714,7 +816,7 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
     for (int cand = kWarpsMax; cand >= kSweepWarpsMin; cand--) {
         plan_sweeps(d, roi, b0, b1, mask, cand, pl);
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (cand + 1) * 32, smem_for(cand)) != cudaSuccess) per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (cand + 2) * 32, smem_for(cand)) != cudaSuccess) per_sm = 0;
         const long long on_busiest = (pl.total_blocks + n_sm - 1) / n_sm;
         // not resident at once: the sweeps run in waves, every wave a whole sweep long
         const long long cost = on_busiest <= per_sm ? on_busiest * cand : (1LL << 40) + on_busiest * cand;
@@ -748,7 +850,7 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
     sc.epoch = sc.epoch % 15 + 1;
     const unsigned e = sc.epoch;
     pl.tagword = ((e & 1u) << 7) | (((e >> 1) & 1u) << 15) | (((e >> 2) & 1u) << 23) | (((e >> 3) & 1u) << 31);
-    k_sgm_sweeps<NR, LPC, FULL, IL><<<(unsigned)pl.total_blocks, (nw + 1) * 32, smem_for(nw), st>>>(fused, d, pl, sc.vols, sc.mailbox, status, 1u);
+    k_sgm_sweeps<NR, LPC, FULL, IL><<<(unsigned)pl.total_blocks, (nw + 2) * 32, smem_for(nw), st>>>(fused, d, pl, sc.vols, sc.mailbox, status, 1u);
     lc.add();
 }
 
