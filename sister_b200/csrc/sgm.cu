@@ -24,7 +24,8 @@
 //     state stays in its chain's registers. The rider's state is handed from chain n-1 to chain n between steps: what chain
 //     n-1 left after step t-1 IS the diagonal predecessor of chain n at step t. The hand-over is one-directional, so the
 //     blocks of a sweep form a pipeline (block b consumes what block b-1 published), never a two-sided wavefront:
-//         inside a block    through shared memory, double-buffered, one block barrier per step;
+//         inside a block    through rings of exchange entries in shared memory guarded by full / empty mbarriers between
+//                           neighbouring warps: warps run free, each just behind the one in front (no block barrier);
 //         between blocks    through a full-length mailbox in global memory (one entry per step; every 32-bit word carries
 //                           the launch's 4-bit epoch tag in the top bits of its bytes -- states are <= P2 < 128 -- so a word
 //                           is valid or not by itself: no flags, no fences, no ring, no back-pressure, and a block that is
@@ -46,7 +47,7 @@ namespace sister {
 
 // compute warps per block (+ 1 mailbox warp): up to 18 while a lane holds few registers of state, fewer for the long
 // disparity ranges, whose state needs the registers a smaller block leaves per thread
-constexpr int sweep_warps_max(int NR) { return NR <= 8 ? 18 : NR <= 12 ? 12 : 8; }
+__host__ __device__ constexpr int sweep_warps_max(int NR) { return NR <= 8 ? 18 : NR <= 12 ? 12 : 8; }
 constexpr int kSweepWarpsMin = 6;  // the mailbox allocation of a context is sized for this many (sgm_mailbox_bytes)
 constexpr int kRing = 8;           // cost ring slots per warp
 constexpr int kSpinLimit = 1 << 21;
@@ -163,15 +164,10 @@ template <int NR, int LPC, bool FULL> __device__ __forceinline__ void entry_stor
     for (int k = 0; k < NR / 2; k++) reinterpret_cast<uint32_t *>(entry)[k * LPC + li.sl] = w[k];
 }
 
-// One step of the rider. Its state travels between chains in the OFFSET DOMAIN: every 16-bit half carries + off, off = 0x100
-// on odd laps of the exchange ring, 0 on even ones -- bit 8 of a half is the entry's phase tag (states are <= P2 + P1 < 256),
-// so every 32-bit word of an entry says by itself whether it belongs to the lap the reader expects. The offset costs
-// nothing: it rides through min / + unchanged, cancels in the normalisation (L' - min L') and is replaced by the writer's
-// own phase in the constants of that same instruction. The state arrives as `a` only, b and the end neighbours are formed
-// here, and the new state leaves as `a` only; q comes out carrying the reader's offset (the caller subtracts it).
+// One step of the rider: the state arrives as `a` only (from the neighbouring chain), b and the end neighbours are formed
+// here, and the new state leaves as `a` only.
 template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ void rider_step(const uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo<NR, LPC, FULL> &li, uint32_t off_out16, uint32_t clamp2,
-                                           uint32_t (&q)[NR], uint32_t (&out)[NR])
+__device__ __forceinline__ void rider_step(const uint32_t (&a)[NR], const uint32_t (&c)[NR], const LaneInfo<NR, LPC, FULL> &li, uint32_t (&q)[NR], uint32_t (&out)[NR])
 {
     uint32_t b[NR], left, right, L[NR];
 #pragma unroll
@@ -183,61 +179,50 @@ __device__ __forceinline__ void rider_step(const uint32_t (&a)[NR], const uint32
         L[k] = li.padded(q[k] + c[k], k);
     }
     const uint32_t mm = chain_min2<LPC>(lane_min<NR>(L));
-    const uint32_t neg2 = __byte_perm(off_out16 - mm, 0u, 0x1010); // (off_out - min) mod 2^16 in both halves
+    const uint32_t neg2 = __byte_perm(0u - mm, 0u, 0x1010);
 #pragma unroll
-    for (int k = 0; k < NR; k++) out[k] = li.padded(__viaddmin_s16x2(L[k], neg2, clamp2), k);
+    for (int k = 0; k < NR; k++) out[k] = li.padded(__viaddmin_s16x2(L[k], neg2, kP2x2), k);
 }
 
-constexpr uint32_t kPhase2 = 0x01000100u; // the phase tag of both halves of a word
-constexpr int kXR = 4;                     // exchange ring: entries per chain boundary (= steps per trip of the step loop)
+// ---- hand-over between the warps of a block: a ring of kXR exchange entries per chain boundary, guarded by one "full" and
+// one "empty" mbarrier per entry of every boundary that separates two warps (chains of one warp are in lock step).
+//   writer (the warp in front), step s:   wait empty[s % kXR] (lap s / kXR) -- write the state it leaves -- arrive full[s % kXR]
+//   reader (the warp behind), step s + 1: wait full[s % kXR]  (lap s / kXR) -- read                       -- arrive empty[s % kXR]
+// Warps run free, each as far behind the one in front as the hand-over takes, never more than kXR - 1 steps ahead of the
+// one behind. The waits are hardware suspends (mbarrier.try_wait), not polls: a waiting warp takes no issue slot.
+constexpr int kXR = 4;       // entries per boundary = steps per trip of the step loop
 
-// the tag bits of register k that hold a disparity (padding halves always read 0x3FFF)
-template <int NR, int LPC, bool FULL> __device__ __forceinline__ uint32_t phase_bits(const LaneInfo<NR, LPC, FULL> &li, int k)
+__device__ __forceinline__ void mbar_init(unsigned bar_s, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar_s), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned bar_s) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_s) : "memory"); }
+// Wait for the phase of parity `parity`. The loop is bounded (a broken pipeline must never hang the device): try_wait
+// suspends the warp in hardware for up to the time hint, so the rounds are few and cost no issue slots while waiting.
+__device__ __forceinline__ bool mbar_wait(unsigned bar_s, unsigned parity, bool &broken)
 {
-    if constexpr (FULL) return kPhase2;
-    else return kPhase2 & ~li.pad[k];
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\tmov.u32 n, 0;\n\t"
+        "MBW_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t@p bra MBW_DONE;\n\t"
+        "add.u32 n, n, 1;\n\tsetp.lt.u32 p, n, 4096;\n\t@p bra MBW_LOOP;\n\t"
+        "mov.u32 %0, 0;\n\tbra MBW_END;\n\tMBW_DONE:\n\tmov.u32 %0, 1;\n\tMBW_END:\n\t}\n"
+        : "=r"(ok) : "r"(bar_s), "r"(parity) : "memory");
+    if (!ok) broken = true;
+    return ok != 0u;
 }
-
-__device__ __forceinline__ uint32_t lds_volatile(unsigned a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void sts32(unsigned a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
-
-// Wait until entry `entry_s` carries the expected phase in every word, and read it. Returns false after kSpinLimit polls
-// (a broken pipeline must never hang the device: the caller reports it and stops waiting).
-template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ bool xch_wait_read(unsigned entry_s, const LaneInfo<NR, LPC, FULL> &li, uint32_t expw, bool on, bool &broken, uint32_t (&a)[NR])
-{
-    int spins = 0;
-    for (;;) {
-        xch_read<NR, LPC>(entry_s, li.sl, a);
-        uint32_t bad = 0u;
-#pragma unroll
-        for (int k = 0; k < NR; k++) bad |= (a[k] ^ expw) & phase_bits<NR, LPC, FULL>(li, k);
-        if (!__any_sync(kFull, on && bad != 0u) || broken) return true;
-        if (++spins > kSpinLimit) { broken = true; return false; }
-    }
-}
-// wait until the reader behind boundary ring `done_s` has read what slot (s mod kXR) held a lap ago
-__device__ __forceinline__ bool xch_wait_free(unsigned done_s, int s, bool &broken)
-{
-    int spins = 0;
-    while ((int)lds_volatile(done_s) < s - (kXR - 2) && !broken)
-        if (++spins > kSpinLimit) { broken = true; return false; }
-    return true;
-}
+// every lane arrives (the barriers count 32 arrivals): no election, no warp synchronisation, and each lane's own writes are
+// released by its own arrival
+__device__ __forceinline__ void warp_arrive(unsigned bar_s, int lane) { (void)lane; mbar_arrive(bar_s); }
+// barriers of warp boundary wb: full[0 .. kXR), empty[0 .. kXR), 8 bytes each
+__device__ __forceinline__ unsigned bar_full(unsigned bars_s, int wb, int e) { return bars_s + (unsigned)((wb * 2 * kXR + e) * 8); }
+__device__ __forceinline__ unsigned bar_empty(unsigned bars_s, int wb, int e) { return bars_s + (unsigned)((wb * 2 * kXR + kXR + e) * 8); }
 
 // ---------------------------------------------------------------------------------------------- the sweep kernel
 
 // MODE 0: carrier + rider; 1: rider only (chains in front of the region); 2: the warp that holds the first line of a row
 // sweep (carrier = the literal first-line arithmetic, rider restarts from the zero state at every step, nothing is read)
-//
-// Hand-over inside a block: boundary e (0 .. chains of the block) is a ring of kXR entries in shared memory; the chain in
-// slot e - 1 writes the state it left after step s into entry s mod kXR with phase (s / kXR) & 1, the chain in slot e polls
-// that entry's phase at step s + 1. No barrier, no fence: warps run free, each as far behind its predecessor as the
-// hand-over takes. A writer must not lap its reader: a warp publishes how many steps' inputs it has read (done[warp]) and the
-// warp in front checks it before every write (chains of one warp are in lock step and need no check).
+// in_wb / out_wb: the warp boundaries this warp reads from / writes to (-1: nobody on the other side)
 template <int NR, int LPC, bool FULL, bool IL, int MODE>
 __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, uint8_t *__restrict__ vol, const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, int D,
-                                           int n, bool alive, bool car, int cl, unsigned ring_s, unsigned x_s, unsigned my_done_s, unsigned cons_done_s, int lane,
+                                           int n, bool alive, bool car, int cl, unsigned ring_s, unsigned x_s, unsigned bars_s, int in_wb, int out_wb, int lane,
                                            int n_sync, int *__restrict__ status)
 {
     constexpr int CPW = 32 / LPC;
@@ -285,9 +270,9 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
     for (int s = 0; s < A; s++) copy_step(s < T, s * SS);
     const unsigned rd_lane = ring_s + sub * DS + li.template cell_offset<IL>();
     unsigned half = 0, other = U * SS;
-    uint32_t phase = 0u; // kPhase2 on odd trips
+    unsigned lap = 0u; // parity of the exchange ring's lap = of the trip
     auto wr_off = [&](const int u) { return u == 0 ? other + (U - 1) * SS : half + (u - 1) * SS; };
-    auto next_trip = [&]() { const unsigned t = half; half = other; other = t; phase ^= kPhase2; };
+    auto next_trip = [&]() { const unsigned t = half; half = other; other = t; lap ^= 1u; };
     // ---- state
     ChainState<NR> cs;
     uint32_t mm = 0; // MODE 2: minimum of the truncated first-line state
@@ -298,30 +283,51 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
     const unsigned x_in = x_s + (unsigned)cl * (kXR * EX), x_out = x_in + kXR * EX; // + entry * EX
     const bool frame_start = g.t0 == 0;
     const long long band_chain = (long long)(n - g.n0) * DS, band_riders = (long long)(g.n1 - g.n0) * DS;
-    {   // shared memory keeps what the previous kernel left: every entry of the ring this chain writes starts in phase 1, the
-        // lap before the first, so that no reader takes stale bytes for the state it is waiting for
-        uint32_t a[NR];
-#pragma unroll
-        for (int k = 0; k < NR; k++) a[k] = kPhase2;
-#pragma unroll
-        for (int e = 0; e < kXR; e++) xch_write<NR, LPC>(x_out + e * EX, li.sl, a);
-    }
     if (!g.row && g.band_in) { // a column sweep continued from the band before: [carrier states | rider states] per chain
         uint32_t a[NR];
         entry_load<NR, LPC, FULL>(g.band_in + band_chain, li, a);
         chain_resume<NR, LPC, FULL>(cs, a, li);
-        // what this chain left after the step before the band: entry kXR - 1 of the lap before the first (phase 1)
-        entry_load<NR, LPC, FULL>(g.band_in + band_riders + band_chain, li, a, kPhase2);
-        xch_write<NR, LPC>(x_out + (kXR - 1) * EX, li.sl, a);
+        // what this chain left after the step before the band: the entry before entry 0
+        entry_load<NR, LPC, FULL>(g.band_in + band_riders + band_chain, li, rider_out);
+        xch_write<NR, LPC>(x_out + (kXR - 1) * EX, li.sl, rider_out);
     }
     uint8_t *dst = vol + (long long)my_off8 * 8 + li.template cell_offset<IL>();
-    block_sync(n_sync); // done[] is zero, the entries of the first step (band states) are in place
+    const unsigned in_full = in_wb >= 0 ? bar_full(bars_s, in_wb, 0) : 0u, in_empty = in_wb >= 0 ? bar_empty(bars_s, in_wb, 0) : 0u;
+    const unsigned out_full = out_wb >= 0 ? bar_full(bars_s, out_wb, 0) : 0u, out_empty = out_wb >= 0 ? bar_empty(bars_s, out_wb, 0) : 0u;
+    block_sync(n_sync); // the barriers are initialised, the entries of the first step (band states) are in place
     bool broken = false;
     // GEN: the general step (first trip, trips that straddle an edge of the stored range, tail); otherwise STORE says whether
     // the whole trip lies inside the stored range, and nothing is tested
     auto step = [&](const int s, const int u, auto gen_tag, auto store_tag) {
         constexpr bool GEN = decltype(gen_tag)::value, STORE = decltype(store_tag)::value;
+        constexpr int kPrev = kXR - 1;
         uint32_t c[NR], q1[NR];
+        // ---- the rider's state: what the neighbouring chain left after step s - 1 (entry (s - 1) mod kXR; lap of step s - 1)
+        uint32_t ra[NR];
+        const int e_in = (u + kPrev) % kXR;
+        if (MODE == 2 || (GEN && frame_start && s == 0)) {
+            // first line: zero state; row sweep at its first column: the predecessor is off the image
+            const uint32_t v = (MODE != 2 && g.row) ? kP2x2 : 0u;
+#pragma unroll
+            for (int k = 0; k < NR; k++) ra[k] = li.padded(v, k);
+            if (GEN && MODE != 2 && s == 0 && in_wb >= 0) { // nothing to read at the first step: every entry starts out free
+#pragma unroll
+                for (int e = 0; e < kXR; e++) mbar_arrive(in_empty + 8u * e);
+            }
+        } else {
+            if (in_wb >= 0 && (!GEN || s > 0)) {
+                if (!mbar_wait(in_full + 8u * e_in, u == 0 ? lap ^ 1u : lap, broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
+            }
+            xch_read<NR, LPC>(x_in + e_in * EX, li.sl, ra);
+            if (in_wb >= 0) {
+                if (GEN && s == 0) { // a band's first step read the entry before entry 0; the others start out free
+#pragma unroll
+                    for (int e = 0; e < kXR; e++) mbar_arrive(in_empty + 8u * e);
+                } else {
+                    mbar_arrive(in_empty + 8u * e_in);
+                }
+            }
+        }
         {
             cp_async_wait<A - 1>();
             __syncwarp();
@@ -336,21 +342,12 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
             unpack_cost<NR, IL>(w, c);
         }
         copy_step(!GEN || s + A < T, wr_off(u));
-        // ---- rider
-        uint32_t ra[NR], off_in = 0u;
-        if (MODE == 2 || (GEN && frame_start && s == 0)) {
-            // first line: zero state; row sweep at its first column: the predecessor is off the image
-            const uint32_t v = (MODE != 2 && g.row) ? kP2x2 : 0u;
-#pragma unroll
-            for (int k = 0; k < NR; k++) ra[k] = li.padded(v, k);
-        } else {
-            off_in = u == 0 ? phase ^ kPhase2 : phase; // the state after step s - 1: previous entry, previous lap for u == 0
-            if (!xch_wait_read<NR, LPC, FULL>(x_in + ((u + kXR - 1) % kXR) * EX, li, off_in, true, broken, ra) && lane == 0) atomicOr(status, kStatusSpinTimeout);
-            if (lane == 0) sts32(my_done_s, (uint32_t)(s + 1));
+        rider_step<NR, LPC, FULL>(ra, c, li, q1, rider_out);
+        if (out_wb >= 0) {
+            if (!mbar_wait(out_empty + 8u * u, lap, broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
         }
-        rider_step<NR, LPC, FULL>(ra, c, li, phase >> 16, kP2x2 + phase, q1, rider_out);
-        if (cons_done_s != 0u && !xch_wait_free(cons_done_s, s, broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
         xch_write<NR, LPC>(x_out + u * EX, li.sl, rider_out);
+        if (out_wb >= 0) warp_arrive(out_full + 8u * u, lane);
         // ---- carrier, sum, store
         if constexpr (MODE != 1) {
             uint32_t q0[NR];
@@ -358,7 +355,7 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
             else chain_step<NR, LPC, FULL>(cs, c, li, q0);
             if (GEN ? (car && (unsigned)(s - ts_lo) < (unsigned)ts_n) : STORE) {
 #pragma unroll
-                for (int k = 0; k < NR; k++) q0[k] = q0[k] + q1[k] - off_in;
+                for (int k = 0; k < NR; k++) q0[k] += q1[k];
                 store_q<NR, LPC, FULL, IL>(dst, q0, valid_bytes);
             }
             dst += step_bytes;
@@ -387,12 +384,8 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
         if (s0 + u < T) step(s0 + u, u, std::true_type{}, std::false_type{}); // warp-uniform
     cp_async_wait<0>();
     if (!g.row && g.band_out && alive) { // leave the column sweep's states for the next band
-        uint32_t a[NR];
-        const uint32_t last_phase = ((T - 1) / kXR) & 1 ? kPhase2 : 0u;
-#pragma unroll
-        for (int k = 0; k < NR; k++) a[k] = rider_out[k] - last_phase;
         entry_store<NR, LPC, FULL>(g.band_out + band_chain, li, cs.a);
-        entry_store<NR, LPC, FULL>(g.band_out + band_riders + band_chain, li, a);
+        entry_store<NR, LPC, FULL>(g.band_out + band_riders + band_chain, li, rider_out);
     }
 }
 
@@ -401,7 +394,7 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
 // entries ahead so that the L2 round trip stays off the consumers' path.
 template <int NR, int LPC, bool FULL>
 __device__ __forceinline__ void import_warp(const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, int b, int ch, const uint8_t *__restrict__ mailbox, unsigned tagword,
-                                            unsigned x_s, unsigned done0_s, int lane, int n_sync, int *__restrict__ status)
+                                            unsigned x_s, unsigned bars_s, int lane, int n_sync, int *__restrict__ status)
 {
     constexpr int NH = NR / 2;
     constexpr int EX = NR * LPC * 4;
@@ -414,23 +407,18 @@ __device__ __forceinline__ void import_warp(const LaneInfo<NR, LPC, FULL> &li, c
     else if (g.row && g.band_in) src = g.band_in; // the band before left one state per step, untagged
     const long long lane_off = (long long)li.sl * 4;
     uint32_t a[NR];
-    if (on) { // boundary 0 starts in phase 1, the lap before the first (see sweep_warp)
-#pragma unroll
-        for (int k = 0; k < NR; k++) a[k] = kPhase2;
-#pragma unroll
-        for (int e = 0; e < kXR; e++) xch_write<NR, LPC>(x_s + e * EX, li.sl, a);
-    }
     if (on && !g.row && g.band_in) {
         // a column sweep continued from the band before: the state the predecessor of the block's first chain left (the
-        // border column has none: P2)
-        if (b > 0) entry_load<NR, LPC, FULL>(g.band_in + ((long long)(g.n1 - g.n0) + (long long)b * ch - 1) * EB, li, a, kPhase2);
+        // border column has none: P2) goes into the entry before entry 0
+        if (b > 0) entry_load<NR, LPC, FULL>(g.band_in + ((long long)(g.n1 - g.n0) + (long long)b * ch - 1) * EB, li, a);
         else {
 #pragma unroll
-            for (int k = 0; k < NR; k++) a[k] = li.padded(kP2x2 + kPhase2, k);
+            for (int k = 0; k < NR; k++) a[k] = li.padded(kP2x2, k);
         }
         xch_write<NR, LPC>(x_s + (kXR - 1) * EX, li.sl, a);
     }
     block_sync(n_sync);
+    const unsigned full0 = bar_full(bars_s, 0, 0), empty0 = bar_empty(bars_s, 0, 0);
     uint32_t pf0[NH], pf1[NH];
     auto fetch = [&](const int s, uint32_t (&w)[NH]) { // entry s of the source: the predecessor's state after step s
         if (on && src && s < T - 1) {
@@ -449,7 +437,6 @@ __device__ __forceinline__ void import_warp(const LaneInfo<NR, LPC, FULL> &li, c
 #pragma unroll 1
     for (int s = 0; s < T - 1; s++) {
         uint32_t w[NH];
-        const uint32_t ph = (s / kXR) & 1 ? kPhase2 : 0u;
 #pragma unroll
         for (int k = 0; k < NH; k++) { w[k] = pf0[k]; pf0[k] = pf1[k]; }
         fetch(s + 2, pf1);
@@ -471,36 +458,38 @@ __device__ __forceinline__ void import_warp(const LaneInfo<NR, LPC, FULL> &li, c
                     for (int k = 0; k < NH; k++) w[k] = ld_relaxed(e + (long long)k * LPC * 4);
                 }
             }
-            words_to_state<NR, LPC, FULL>(w, li, a, ph);
+            words_to_state<NR, LPC, FULL>(w, li, a);
         } else {
 #pragma unroll
-            for (int k = 0; k < NR; k++) a[k] = li.padded(kP2x2 + ph, k); // the border column of a column sweep
+            for (int k = 0; k < NR; k++) a[k] = li.padded(kP2x2, k); // the border column of a column sweep
         }
-        if (!xch_wait_free(done0_s, s, broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
+        if (!mbar_wait(empty0 + 8u * (s % kXR), (unsigned)((s / kXR) & 1), broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
         if (on) xch_write<NR, LPC>(x_s + (s % kXR) * EX, li.sl, a);
+        warp_arrive(full0 + 8u * (s % kXR), lane);
     }
 }
 
 // The export warp of a block: publishes the rider states the block's last chain leaves, one mailbox (or band) entry per step.
 template <int NR, int LPC, bool FULL>
 __device__ __forceinline__ void export_warp(const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, uint8_t *__restrict__ dst, unsigned dst_tag, unsigned x_last,
-                                            unsigned my_done_s, int lane, int n_sync, int *__restrict__ status)
+                                            unsigned bars_s, int wb, int lane, int n_sync, int *__restrict__ status)
 {
     constexpr int NH = NR / 2;
     constexpr int EX = NR * LPC * 4;
     constexpr long long EB = 2 * NR * LPC;
     const int T = g.t1 - g.t0;
     const bool on = lane < LPC;
+    const unsigned full = bar_full(bars_s, wb, 0), empty = bar_empty(bars_s, wb, 0);
     block_sync(n_sync);
+#pragma unroll
+    for (int e = 0; e < kXR; e++) mbar_arrive(empty + 8u * e); // every entry starts out free
     bool broken = false;
 #pragma unroll 1
     for (int s = 0; s < T; s++) {
         uint32_t a[NR], w[NH];
-        const uint32_t ph = (s / kXR) & 1 ? kPhase2 : 0u;
-        if (!xch_wait_read<NR, LPC, FULL>(x_last + (s % kXR) * EX, li, ph, on, broken, a) && lane == 0) atomicOr(status, kStatusSpinTimeout);
-        if (lane == 0) sts32(my_done_s, (uint32_t)(s + 2)); // as a reader this warp is at the step after the one it publishes
-#pragma unroll
-        for (int k = 0; k < NR; k++) a[k] -= ph;
+        if (!mbar_wait(full + 8u * (s % kXR), (unsigned)((s / kXR) & 1), broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
+        xch_read<NR, LPC>(x_last + (s % kXR) * EX, li.sl, a);
+        warp_arrive(empty + 8u * (s % kXR), lane);
         state_to_words<NR>(a, dst_tag, w);
         if (on) {
             uint8_t *e = dst + (long long)s * EB + (long long)li.sl * 4;
@@ -537,9 +526,9 @@ __global__ void __launch_bounds__((sweep_warps_max(NR) + 2) * 32)
     li.init(lane, d.D);
     opaque(li.up_mask); opaque(li.dn_mask);
     li.one = one; // a kernel argument: the only 1 neither nvvm nor ptxas can fold (add_fma)
-    // shared memory: done[nw + 2] words, the exchange rings of CH + 1 boundaries, the warps' cost rings
-    const unsigned done_s = (unsigned)__cvta_generic_to_shared(smem_raw);
-    const unsigned x_s = done_s + 128u;
+    // shared memory: the barriers of nw + 1 warp boundaries, the exchange rings of CH + 1 chain boundaries, the warps' cost rings
+    const unsigned bars_s = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned x_s = bars_s + (unsigned)((sweep_warps_max(NR) + 1) * 2 * kXR * 8);
     const unsigned rings_s = x_s + (unsigned)(CH + 1) * (kXR * EX);
     // who feeds boundary 0, who drains the last boundary
     const bool first_line_block = g.row && g.n0 == 0 && b == 0; // its first warp holds the first line and reads nothing
@@ -549,18 +538,21 @@ __global__ void __launch_bounds__((sweep_warps_max(NR) + 2) * 32)
     if (b < g.nblk - 1) { dst = mailbox + (g.mb_off + (long long)b * T) * EB; dst_tag = pl.tagword; }
     else if (g.row && g.band_out) dst = g.band_out;
     const int n_sync = (n_live + (has_import ? 1 : 0) + (dst ? 1 : 0)) * 32;
-    if (threadIdx.x < 32) sts32(done_s + 4u * threadIdx.x, 0u); // (nw + 2 <= 20 counters)
+    for (int k = threadIdx.x; k < (n_live + 1) * 2 * kXR; k += blockDim.x) mbar_init(bars_s + 8u * k, 32); // the 32 lanes of one arriving warp each
     if (warp == nw) {
-        if (has_import) import_warp<NR, LPC, FULL>(li, g, b, CH, mailbox, pl.tagword, x_s, done_s, lane, n_sync, status);
+        if (has_import) import_warp<NR, LPC, FULL>(li, g, b, CH, mailbox, pl.tagword, x_s, bars_s, lane, n_sync, status);
         return;
     }
     if (warp == nw + 1) {
-        if (dst) export_warp<NR, LPC, FULL>(li, g, dst, dst_tag, x_s + (unsigned)last_e * (kXR * EX), done_s + 4u * (unsigned)nw, lane, n_sync, status);
+        if (dst) export_warp<NR, LPC, FULL>(li, g, dst, dst_tag, x_s + (unsigned)last_e * (kXR * EX), bars_s, n_live, lane, n_sync, status);
         return;
     }
     if (warp >= n_live) return;
+    // The scheduler prefers the warp with the highest id. A pipeline drains when its consumers are served first, so the
+    // chains are dealt to the warps in reverse: warp n_live - 1 is the first stage (position 0) and warp 0 the last.
+    const int pos = n_live - 1 - warp;
     const int sub = lane / LPC;
-    const int cl = warp * CPW + sub;        // slot within the block
+    const int cl = pos * CPW + sub;         // slot within the block
     const int u = b * CH + cl;              // slot within the sweep
     int n = g.n0 + u - g.lead;
     const bool alive = u >= g.lead && n < g.n1;
@@ -568,16 +560,15 @@ __global__ void __launch_bounds__((sweep_warps_max(NR) + 2) * 32)
     const bool car = alive && n >= g.car0 && n < g.car1;
     const unsigned ring_s = rings_s + (unsigned)warp * (kRing * CPW * 2 * NR * LPC);
     uint8_t *vol = vols + (size_t)g.vol * (size_t)d.cells;
-    // the reader behind this warp's last boundary: the next warp, or the export warp when the block's last chain is here
-    unsigned cons_done_s = 0u;
-    if (warp + 1 < n_live) cons_done_s = done_s + 4u * (unsigned)(warp + 1);
-    else if (dst) cons_done_s = done_s + 4u * (unsigned)nw;
-    const unsigned my_done_s = done_s + 4u * (unsigned)warp;
-    const bool first_line_warp = first_line_block && warp == 0; // holds chain 0 in its last sub-chain, the others are dead
+    // warp boundary w separates warp w - 1 (or the import warp) from warp w; boundary n_live separates the last warp from
+    // the export warp
+    const int in_wb = (pos > 0 || has_import) ? pos : -1;
+    const int out_wb = (pos + 1 < n_live || dst) ? pos + 1 : -1;
+    const bool first_line_warp = first_line_block && pos == 0; // holds chain 0 in its last sub-chain, the others are dead
     const bool any_car = __any_sync(kFull, car);
-    if (first_line_warp) sweep_warp<NR, LPC, FULL, IL, 2>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, my_done_s, cons_done_s, lane, n_sync, status);
-    else if (!any_car) sweep_warp<NR, LPC, FULL, IL, 1>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, my_done_s, cons_done_s, lane, n_sync, status);
-    else sweep_warp<NR, LPC, FULL, IL, 0>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, my_done_s, cons_done_s, lane, n_sync, status);
+    if (first_line_warp) sweep_warp<NR, LPC, FULL, IL, 2>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, bars_s, in_wb, out_wb, lane, n_sync, status);
+    else if (!any_car) sweep_warp<NR, LPC, FULL, IL, 1>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, bars_s, in_wb, out_wb, lane, n_sync, status);
+    else sweep_warp<NR, LPC, FULL, IL, 0>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, bars_s, in_wb, out_wb, lane, n_sync, status);
 }
 
 // ---------------------------------------------------------------------------------------------- final sum + WTA + encode
@@ -799,7 +790,7 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
 {
     constexpr int CPW = 32 / LPC;
     const void *kernel = (const void *)k_sgm_sweeps<NR, LPC, FULL, IL>;
-    auto smem_for = [&](int nw) { return (size_t)128 + (size_t)kXR * (nw * CPW + 1) * NR * LPC * 4 + (size_t)nw * kRing * CPW * 2 * NR * LPC; };
+    auto smem_for = [&](int nw) { return (size_t)(sweep_warps_max(NR) + 1) * 2 * kXR * 8 + (size_t)kXR * (nw * CPW + 1) * NR * LPC * 4 + (size_t)nw * kRing * CPW * 2 * NR * LPC; };
     constexpr int kWarpsMax = sweep_warps_max(NR);
     if (smem_for(kWarpsMax) > 48 * 1024) lc.fail(optin_dynamic_smem(kernel, smem_for(kWarpsMax)));
     // Compute warps per block. The blocks of a sweep are a pipeline: it runs at the pace of its slowest block, and a block's
