@@ -25,17 +25,19 @@ def shard_counts(n_rigs: int, world: int) -> List[int]:
     return [frame_shard(n_rigs, world, r)[1] - frame_shard(n_rigs, world, r)[0] for r in range(world)]
 
 
-def gather_maps(local_maps, n_rigs: int, dst: int = 0, group=None):
+def gather_maps(local_maps, n_rigs: int, dst: int = 0, group=None, async_op: bool = False):
     """Gather every rank's [n_local, H, W] maps (torch int16 tensor holding the uint16 bit patterns; NCCL has no u16)
     to rank `dst` in rig order. Returns the [n_rigs, H, W] tensor on dst, None elsewhere. Blocks are padded to the
-    largest shard so a single collective moves everything."""
+    largest shard so a single collective moves everything.
+    async_op: start the collective and return a function that completes it (and returns the same result), so that the
+    caller can compute the next batch while the maps travel."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     if world == 1:
-        return local_maps
+        return (lambda: local_maps) if async_op else local_maps
     counts = shard_counts(n_rigs, world)
     cap = max(counts)
     h, w = local_maps.shape[1:]
@@ -46,10 +48,16 @@ def gather_maps(local_maps, n_rigs: int, dst: int = 0, group=None):
     # the collective moves bytes: neither NCCL nor gloo carries 16-bit integers on every op
     send = send.contiguous().view(torch.uint8)
     recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
-    dist.gather(send, recv, dst=dst, group=group)
-    if rank != dst:
-        return None
-    return torch.cat([recv[r][: counts[r]] for r in range(world)], dim=0).view(local_maps.dtype)
+    work = dist.gather(send, recv, dst=dst, group=group, async_op=async_op)
+
+    def finish():
+        if work is not None:
+            work.wait()
+        if rank != dst:
+            return None
+        return torch.cat([recv[r][: counts[r]] for r in range(world)], dim=0).view(local_maps.dtype)
+
+    return finish if async_op else finish()
 
 
 def compute_sharded(compute_block: Callable[[Sequence[int]], "object"], n_rigs: int, gather_to: int | None = 0, group=None):
