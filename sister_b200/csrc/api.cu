@@ -25,6 +25,8 @@ struct Slot {
     unsigned long long *d_census = nullptr;
     int16_t *d_wtaL = nullptr, *d_wtaR = nullptr, *d_medL = nullptr, *d_medR = nullptr, *d_lr = nullptr;
     uint8_t *d_masks = nullptr, *d_fused = nullptr;
+    const uint8_t *last_fused = nullptr; // fused volume of the last mode run (SISTER_TAP_FUSED)
+    uint8_t *d_fused_hv = nullptr; // the horizontal-pair and vertical-pair volumes of a call that asks for several modes (allocated on first use)
     SgmScratch sgm;             // four one-byte pair volumes + the sweeps' mailbox (sgm.cu)
     uint16_t *d_sum = nullptr;  // aggregated volume, allocated only while the test taps are enabled
     int16_t *d_raw = nullptr;
@@ -150,14 +152,31 @@ int run_pipeline(sister_ctx *ctx, Slot &s, const uint8_t *const in_views[5], int
     begin_stage(ctx, s, SISTER_STAGE_MASK);
     launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, view_mask, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.st, ctx->lc);
     end_stage(ctx, s);
+    // Several modes in one call (the reference class always runs all three, hpp:77-89): one fuse pass evaluates every Hamming
+    // distance once and writes the horizontal, the vertical and the multiview (their sum, hpp:262-276) volume together.
+    const bool several = (mode_mask & (mode_mask - 1)) != 0;
+    if (several && !s.d_fused_hv) {
+        const cudaError_t e = cudaMalloc((void **)&s.d_fused_hv, (size_t)2 * ctx->cells_max);
+        if (e != cudaSuccess) { cudaGetLastError(); s.d_fused_hv = nullptr; } // no room: fall back to one pass per mode
+    }
+    const bool triple = several && s.d_fused_hv;
+    if (triple) {
+        begin_stage(ctx, s, SISTER_STAGE_FUSE);
+        launch_fuse(s.d_census, s.d_masks, d, 0xFu, s.d_fused, s.d_status, s.st, ctx->lc, 0, -1, s.d_fused_hv, s.d_fused_hv + (size_t)ctx->cells_max);
+        end_stage(ctx, s);
+    }
     for (int mode = 0; mode < 3; mode++) {
         if (!(mode_mask & (1u << mode))) continue;
         const unsigned vm = mode == 0 ? 0xFu : mode == 1 ? 0x3u : 0xCu; // hpp:262-276
-        begin_stage(ctx, s, SISTER_STAGE_FUSE);
-        launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused, s.d_status, s.st, ctx->lc);
-        end_stage(ctx, s);
+        const uint8_t *fused_of_mode = !triple || mode == 0 ? s.d_fused : s.d_fused_hv + (size_t)(mode - 1) * (size_t)ctx->cells_max;
+        if (!triple) {
+            begin_stage(ctx, s, SISTER_STAGE_FUSE);
+            launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused, s.d_status, s.st, ctx->lc);
+            end_stage(ctx, s);
+        }
+        s.last_fused = fused_of_mode;
         begin_stage(ctx, s, SISTER_STAGE_AGGREGATE);
-        launch_sgm(s.d_fused, d, ctx->full_frame || ctx->taps, s.sgm, ctx->taps ? s.d_sum : nullptr, s.d_raw + (size_t)mode * d.px,
+        launch_sgm(fused_of_mode, d, ctx->full_frame || ctx->taps, s.sgm, ctx->taps ? s.d_sum : nullptr, s.d_raw + (size_t)mode * d.px,
                    out_dev ? out_dev[mode] : nullptr, s.d_status, s.st, ctx->lc);
         end_stage(ctx, s);
     }
@@ -176,7 +195,7 @@ void free_slot(Slot &s)
     if (s.st) cudaStreamSynchronize(s.st);
     cudaFree(s.d_in); cudaFreeHost(s.h_in); cudaFree(s.d_oriented); cudaFree(s.d_census);
     cudaFree(s.d_wtaL); cudaFree(s.d_wtaR); cudaFree(s.d_medL); cudaFree(s.d_medR); cudaFree(s.d_lr);
-    cudaFree(s.d_masks); cudaFree(s.d_fused); cudaFree(s.sgm.vols); cudaFree(s.sgm.mailbox); cudaFree(s.d_sum); cudaFree(s.d_raw); cudaFree(s.d_out);
+    cudaFree(s.d_masks); cudaFree(s.d_fused); cudaFree(s.d_fused_hv); cudaFree(s.sgm.vols); cudaFree(s.sgm.mailbox); cudaFree(s.d_sum); cudaFree(s.d_raw); cudaFree(s.d_out);
     cudaFreeHost(s.h_out); cudaFree(s.d_status); cudaFreeHost(s.h_status);
     for (auto e : s.ev_b) cudaEventDestroy(e);
     for (auto e : s.ev_e) cudaEventDestroy(e);
@@ -442,6 +461,7 @@ int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev
     launch_match_wta(s.d_census, d, vm, s.d_wtaL, s.d_wtaR, s.st, ctx->lc);
     launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, vm, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.st, ctx->lc);
     launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused, s.d_status, s.st, ctx->lc, band_row0, band_row1);
+    s.last_fused = s.d_fused;
     SCK(cudaGetLastError());
     SCK(take_launch_error(ctx));
     s.dims = d;
@@ -659,7 +679,7 @@ int sister_debug_fetch(sister_ctx *ctx, int slot, int what, void *host_dst, size
     case SISTER_TAP_WTA_R: src = s.d_wtaR; have = 4 * px * 2; break;
     case SISTER_TAP_LR_FINAL: src = s.d_lr; have = 4 * px * 2; break;
     case SISTER_TAP_MASKS: src = s.d_masks; have = 4 * px; break;
-    case SISTER_TAP_FUSED: src = s.d_fused; have = cells; break;
+    case SISTER_TAP_FUSED: src = s.last_fused ? s.last_fused : s.d_fused; have = cells; break;
     case SISTER_TAP_SUM:
         if (!ctx->taps || !s.d_sum) { ctx->err = "SISTER_TAP_SUM needs sister_set_test_taps(ctx, 1) before the submit"; return SISTER_E_ARG; }
         src = s.d_sum; have = cells * 2; break;
@@ -717,6 +737,7 @@ int sister_stereo(sister_ctx *ctx, const uint8_t *center, const uint8_t *side, i
     ctx->lc.cur_stage = SISTER_STAGE_FUSE;
     SCK(cudaMemsetAsync(s.d_masks, 1, px, s.st));
     launch_fuse(s.d_census, s.d_masks, d, 0x1u, s.d_fused, s.d_status, s.st, ctx->lc);
+    s.last_fused = s.d_fused;
     // SGM (hpp:135) + WTA-left (hpp:137) in the final sweep; the aggregated volume is kept for WTA-right (hpp:138)
     ctx->lc.cur_stage = SISTER_STAGE_AGGREGATE;
     launch_sgm(s.d_fused, d, true, s.sgm, s.d_sum, s.d_wtaL, nullptr, s.d_status, s.st, ctx->lc);

@@ -52,8 +52,11 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
                             int16_t *medR, int16_t *lr_final, uint8_t *masks, cudaStream_t st, LaunchCounter &lc);
 // fused volume C = sum_v mask_v * cost_v as uint8 (hpp:255-277); view_mask selects the mode's views
 // row_lo / row_hi: image rows to produce (whole tiles; the full frame is 0, Hp)
+// fused_h / fused_v (both or neither, with view_mask 0xF): the same pass also writes the fused volumes of the horizontal
+// pair (mode 1) and of the vertical pair (mode 2); `fused` then holds their sum, the multiview volume of mode 0
 void launch_fuse(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
-                 int *status, cudaStream_t st, LaunchCounter &lc, int row_lo = 0, int row_hi = -1);
+                 int *status, cudaStream_t st, LaunchCounter &lc, int row_lo = 0, int row_hi = -1, uint8_t *fused_h = nullptr,
+                 uint8_t *fused_v = nullptr);
 
 // ---- sgm.cu ----
 // Aggregation scratch of one slot: the four pair volumes (4 * cells bytes) and the mailbox through which the blocks of a

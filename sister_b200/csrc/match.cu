@@ -406,9 +406,14 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
 // grid (ceil(Wp/T), ceil(Hp/T)), block 32 * T, dynamic smem 4 * T * (T + D) u64 + 4 * T * T u64 + T * T bytes
 // ORDER: 0 = the cell's byte order is read from Dims at run time; 1 = natural; 2 = lane-interleaved with lpc 16 and
 // nr = NK (D = 32 * nr: the per-k disparity offsets are then compile-time constants and fold into the load addresses)
-template <int T, int NK, int ORDER> // NK = D / 32 when D is a multiple of 32 (fully unrolled), 0 = any D
+// TRIPLE: one pass produces the fused volumes of all three modes (hpp:262-276): the horizontal pair (right + left) into
+// fused_h, the vertical pair (top + bottom) into fused_v and their sum, the multiview volume, into fused -- every Hamming
+// distance is evaluated once instead of once per mode that contains its view. The two partial sums ride in the two halves
+// of one accumulator (<= 2 * 255 each).
+template <int T, int NK, int ORDER, bool TRIPLE> // NK = D / 32 when D is a multiple of 32 (fully unrolled), 0 = any D
 __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__restrict__ census, const uint8_t *__restrict__ masks,
-                                                 Dims d, unsigned view_mask, uint8_t *__restrict__ fused, int *__restrict__ status, int row_lo)
+                                                 Dims d, unsigned view_mask, uint8_t *__restrict__ fused, uint8_t *__restrict__ fused_h,
+                                                 uint8_t *__restrict__ fused_v, int *__restrict__ status, int row_lo)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned s_any;
@@ -516,12 +521,17 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
             for (int k = 0; k < NKC; k++) koff[k] = 8u * (unsigned)dku(k);
             unsigned c1a = c1_base + 8u * (unsigned)(li * T); // + 8 * (v * T * T + lj)
             uint8_t *dst = fused + ((size_t)i * d.Wp + j0) * D;
+            const ptrdiff_t to_h = TRIPLE ? fused_h - fused : 0, to_v = TRIPLE ? fused_v - fused : 0;
 #pragma unroll 1
             for (int lj = 0; lj < T; lj++, dst += D, c1a += 8u) {
                 const unsigned m = smask[li * T + lj];
                 if (m == 0) { // warp-uniform; D is a multiple of 32 here: the cell is D / 16 aligned 16-byte stores
-                    if (lane < D / 16) *reinterpret_cast<uint4 *>(dst + 16 * lane) = make_uint4(0u, 0u, 0u, 0u);
-                    if (NK > 2 && lane + 32 < D / 16) *reinterpret_cast<uint4 *>(dst + 16 * (lane + 32)) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int vol = 0; vol < (TRIPLE ? 3 : 1); vol++) {
+                        uint8_t *z = dst + (vol == 1 ? to_h : vol == 2 ? to_v : 0);
+                        if (lane < D / 16) *reinterpret_cast<uint4 *>(z + 16 * lane) = make_uint4(0u, 0u, 0u, 0u);
+                        if (NK > 2 && lane + 32 < D / 16) *reinterpret_cast<uint4 *>(z + 16 * (lane + 32)) = make_uint4(0u, 0u, 0u, 0u);
+                    }
                 } else {
                     unsigned acc[NKC];
                     if (m == 0xFu) { // all four views (the common case of mode 0): straight-line, no per-view branches
@@ -530,13 +540,15 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
                         for (int v = 0; v < 4; v++) c1[v] = lds64(c1a + 8u * (unsigned)(v * T * T));
 #pragma unroll
                         for (int k = 0; k < NKC; k++) {
-                            unsigned a = 0;
+                            unsigned a = 0, b = 0;
 #pragma unroll
                             for (int v = 0; v < 4; v++) {
                                 const uint2 x = lds64(pv[v] - koff[k]);
-                                a += __popc(x.x ^ c1[v].x) + __popc(x.y ^ c1[v].y);
+                                const unsigned cst = __popc(x.x ^ c1[v].x) + __popc(x.y ^ c1[v].y);
+                                if (TRIPLE && v >= 2) b += cst;
+                                else a += cst;
                             }
-                            acc[k] = a;
+                            acc[k] = TRIPLE ? b * 65536u + a : a;
                         }
                     } else {
 #pragma unroll
@@ -548,20 +560,34 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
 #pragma unroll
                             for (int k = 0; k < NKC; k++) {
                                 const uint2 x = lds64(pv[v] - koff[k]);
-                                acc[k] += __popc(x.x ^ c1.x) + __popc(x.y ^ c1.y);
+                                acc[k] += (__popc(x.x ^ c1.x) + __popc(x.y ^ c1.y)) << ((TRIPLE && v >= 2) ? 16 : 0);
                             }
                         }
                     }
-                    unsigned all = acc[0];
+                    if constexpr (TRIPLE) {
+                        unsigned all = 0;
 #pragma unroll
-                    for (int k = 1; k < NKC; k++) all |= acc[k];
-                    if (all > 255u) { // cannot happen; kept as the literal formula's saturation + flag
-                        overflow = true;
+                        for (int k = 0; k < NKC; k++) all |= (acc[k] & 0xFFFFu) + (acc[k] >> 16);
+                        if (all > 255u) overflow = true; // cannot happen: flagged, bytes saturate below
 #pragma unroll
-                        for (int k = 0; k < NKC; k++) acc[k] = min(acc[k], 255u);
+                        for (int k = 0; k < NKC; k++) {
+                            const unsigned h = acc[k] & 0xFFFFu, v2 = acc[k] >> 16;
+                            dst[lane + 32 * k] = (uint8_t)min(h + v2, 255u);
+                            dst[to_h + lane + 32 * k] = (uint8_t)min(h, 255u);
+                            dst[to_v + lane + 32 * k] = (uint8_t)min(v2, 255u);
+                        }
+                    } else {
+                        unsigned all = acc[0];
+#pragma unroll
+                        for (int k = 1; k < NKC; k++) all |= acc[k];
+                        if (all > 255u) { // cannot happen; kept as the literal formula's saturation + flag
+                            overflow = true;
+#pragma unroll
+                            for (int k = 0; k < NKC; k++) acc[k] = min(acc[k], 255u);
+                        }
+#pragma unroll
+                        for (int k = 0; k < NKC; k++) dst[lane + 32 * k] = (uint8_t)acc[k];
                     }
-#pragma unroll
-                    for (int k = 0; k < NKC; k++) dst[lane + 32 * k] = (uint8_t)acc[k];
                 }
 #pragma unroll
                 for (int v = 0; v < 4; v++) pv[v] += (unsigned)pstep[v];
@@ -594,7 +620,7 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
                 for (int k = 0; k < NKC; k++) {
                     if (NK > 0 || lane + 32 * k < D) {
                         const uint2 x = *reinterpret_cast<const uint2 *>(p - dku(k));
-                        acc[k] += __popc(x.x ^ c1lo) + __popc(x.y ^ c1hi);
+                        acc[k] += (__popc(x.x ^ c1lo) + __popc(x.y ^ c1hi)) << ((TRIPLE && v >= 2) ? 16 : 0);
                     }
                 }
             } else {
@@ -611,7 +637,7 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
                     if (rv < 3) cst = kInvalidCost;
                     else if (!popc_row) cst = 0;
                     else cst = (dd > cc) ? (unsigned)kInvalidCost : (unsigned)__popcll(c1 ^ line[-dd]);
-                    acc[k] += cst;
+                    acc[k] += cst << ((TRIPLE && v >= 2) ? 16 : 0);
                 }
             }
         }
@@ -619,9 +645,17 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
 #pragma unroll
         for (int k = 0; k < NKC; k++) {
             if (NK > 0 || lane + 32 * k < D) {
-                unsigned sum = acc[k];
-                if (sum > 255u) { overflow = true; sum = 255u; }
-                dst[32 * k] = (uint8_t)sum;
+                if constexpr (TRIPLE) {
+                    const unsigned h = acc[k] & 0xFFFFu, v2 = acc[k] >> 16;
+                    if (h + v2 > 255u) overflow = true;
+                    dst[32 * k] = (uint8_t)min(h + v2, 255u);
+                    fused_h[pix * D + lane + 32 * k] = (uint8_t)min(h, 255u);
+                    fused_v[pix * D + lane + 32 * k] = (uint8_t)min(v2, 255u);
+                } else {
+                    unsigned sum = acc[k];
+                    if (sum > 255u) { overflow = true; sum = 255u; }
+                    dst[32 * k] = (uint8_t)sum;
+                }
             }
         }
     }
@@ -630,42 +664,47 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
 
 template <int T, int NK, int ORDER>
 static void launch_fuse_o(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
-                          int *status, cudaStream_t st, int row_lo, int row_hi, LaunchCounter &lc)
+                          uint8_t *fused_h, uint8_t *fused_v, int *status, cudaStream_t st, int row_lo, int row_hi, LaunchCounter &lc)
 {
     const size_t smem = (size_t)4 * T * (T + d.D) * 8 + (size_t)4 * T * T * 8 + T * T;
-    lc.fail(optin_dynamic_smem((const void *)k_fuse<T, NK, ORDER>, smem));
     dim3 grid((d.Wp + T - 1) / T, (row_hi - row_lo + T - 1) / T);
-    k_fuse<T, NK, ORDER><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, status, row_lo);
+    if (fused_h && fused_v) {
+        lc.fail(optin_dynamic_smem((const void *)k_fuse<T, NK, ORDER, true>, smem));
+        k_fuse<T, NK, ORDER, true><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, fused_h, fused_v, status, row_lo);
+        return;
+    }
+    lc.fail(optin_dynamic_smem((const void *)k_fuse<T, NK, ORDER, false>, smem));
+    k_fuse<T, NK, ORDER, false><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, nullptr, nullptr, status, row_lo);
 }
 
 template <int T, int NK>
 static void launch_fuse_t(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
-                          int *status, cudaStream_t st, int row_lo, int row_hi, LaunchCounter &lc)
+                          uint8_t *fused_h, uint8_t *fused_v, int *status, cudaStream_t st, int row_lo, int row_hi, LaunchCounter &lc)
 {
-    if (NK > 0 && d.interleaved && d.lpc == 16 && d.nr == NK) launch_fuse_o<T, NK, (NK > 0 ? 2 : 0)>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc);
-    else if (NK > 0 && !d.interleaved) launch_fuse_o<T, NK, (NK > 0 ? 1 : 0)>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc);
-    else launch_fuse_o<T, NK, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc);
+    if (NK > 0 && d.interleaved && d.lpc == 16 && d.nr == NK) launch_fuse_o<T, NK, (NK > 0 ? 2 : 0)>(census, masks, d, view_mask, fused, fused_h, fused_v, status, st, row_lo, row_hi, lc);
+    else if (NK > 0 && !d.interleaved) launch_fuse_o<T, NK, (NK > 0 ? 1 : 0)>(census, masks, d, view_mask, fused, fused_h, fused_v, status, st, row_lo, row_hi, lc);
+    else launch_fuse_o<T, NK, 0>(census, masks, d, view_mask, fused, fused_h, fused_v, status, st, row_lo, row_hi, lc);
 }
 
 void launch_fuse(const unsigned long long *census, const uint8_t *masks, const Dims &d, unsigned view_mask, uint8_t *fused,
-                 int *status, cudaStream_t st, LaunchCounter &lc, int row_lo, int row_hi)
+                 int *status, cudaStream_t st, LaunchCounter &lc, int row_lo, int row_hi, uint8_t *fused_h, uint8_t *fused_v)
 {
     if (row_hi < 0) row_hi = d.Hp;
     if (row_hi <= row_lo) return;
     // 16 x 16 tiles while two blocks fit an SM (D <= 200), else 8 x 8
     if (d.D <= 200) {
         switch (d.D) {
-        case 64: launch_fuse_t<16, 2>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
-        case 128: launch_fuse_t<16, 4>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
-        case 192: launch_fuse_t<16, 6>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
-        default: launch_fuse_t<16, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
+        case 64: launch_fuse_t<16, 2>(census, masks, d, view_mask, fused, fused_h, fused_v, status, st, row_lo, row_hi, lc); break;
+        case 128: launch_fuse_t<16, 4>(census, masks, d, view_mask, fused, fused_h, fused_v, status, st, row_lo, row_hi, lc); break;
+        case 192: launch_fuse_t<16, 6>(census, masks, d, view_mask, fused, fused_h, fused_v, status, st, row_lo, row_hi, lc); break;
+        default: launch_fuse_t<16, 0>(census, masks, d, view_mask, fused, fused_h, fused_v, status, st, row_lo, row_hi, lc); break;
         }
     } else {
         switch (d.D) {
-        case 256: launch_fuse_t<8, 8>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
-        case 384: launch_fuse_t<8, 12>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
-        case 512: launch_fuse_t<8, 16>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
-        default: launch_fuse_t<8, 0>(census, masks, d, view_mask, fused, status, st, row_lo, row_hi, lc); break;
+        case 256: launch_fuse_t<8, 8>(census, masks, d, view_mask, fused, fused_h, fused_v, status, st, row_lo, row_hi, lc); break;
+        case 384: launch_fuse_t<8, 12>(census, masks, d, view_mask, fused, fused_h, fused_v, status, st, row_lo, row_hi, lc); break;
+        case 512: launch_fuse_t<8, 16>(census, masks, d, view_mask, fused, fused_h, fused_v, status, st, row_lo, row_hi, lc); break;
+        default: launch_fuse_t<8, 0>(census, masks, d, view_mask, fused, fused_h, fused_v, status, st, row_lo, row_hi, lc); break;
         }
     }
     lc.add();

@@ -79,6 +79,23 @@ def test_every_stage_against_oracle(engine, oracle_lib, w, h, D, kind, seed, col
     assert (masks == t["masks"]).all()
 
 
+def test_one_fuse_pass_for_several_modes(engine, oracle_lib):
+    """A call that asks for several modes fuses once: the horizontal, vertical and multiview volumes leave one pass
+    (hpp:262-276: C_mv = C_h + C_v). The volume of the last mode run and every map must be those of the per-mode passes."""
+    views = make_rig(88, 72, 40, seed=17, kind="smooth", channels=3, colour=True)
+    D, hp, wp = 40, 72 + 80, 88 + 80
+    pads = [oracle_lib.pad_replicate(oracle_lib.grey_bgr(v), D) for v in views]
+    for mask, last in ((7, 2), (3, 1), (5, 2), (6, 2)):
+        outs = engine.compute(views, D, mode_mask=mask)
+        t = oracle_lib.multistereo(pads, D, last)
+        fused = engine.fetch("fused", (hp, wp, D), np.uint8)
+        assert (fused == t["fused"]).all(), f"fused volume of mode {last} from the shared pass (mode_mask {mask})"
+        for m in range(3):
+            if (mask >> m) & 1:
+                single = engine.compute(views, D, mode_mask=1 << m)[m]
+                assert (outs[m] == single).all(), f"mode {m} of mode_mask {mask}"
+
+
 def test_sgm_known_answers(engine, oracle_lib):
     k = np.load(os.path.join(GOLDEN, "stage_kats.npz"))
     for i in range(3):
