@@ -60,8 +60,9 @@ typedef struct sister_ctx sister_ctx;
 
 /* Create a context on CUDA device `device` able to process rigs up to max_w x max_h with up to
  * max_disp disparities, with n_slots rigs in flight (each slot owns a stream, pinned staging and all
- * scratch volumes: about (9 * cells + 140 * pixels) bytes, cells = (w+2D)(h+2D)D: the uint8 fused volume
- * and eight uint8 path volumes; 3.9 GB at 1280 x 960 x 192). */
+ * scratch volumes: about (5.3 * cells + 140 * pixels) bytes, cells = (w+2D)(h+2D)D: the uint8 fused volume,
+ * four uint8 pair volumes of the aggregation and its block-to-block mailbox; 2.6 GB at 1280 x 960 x 192; a call that
+ * asks for several modes adds 2 * cells on first use). */
 int sister_create(sister_ctx **ctx, int device, int max_w, int max_h, int max_disp, int n_slots);
 int sister_destroy(sister_ctx *ctx);
 
@@ -128,27 +129,34 @@ int sister_stereo(sister_ctx *ctx, const uint8_t *center, const uint8_t *side, i
  * Row bands: ONE large frame split over several GPUs (BASELINE.json configs[3]).
  * Each GPU (one context per GPU, one process per GPU) owns the rows [band_row0, band_row1) of the PADDED frame
  * (0 .. h + 2 * disp_count). What is split is everything that is a volume: the fused cost (hpp:255-277), the
- * eight SGM path volumes and the final sum / WTA (sgm.cpp:26-455, hpp:283) -- all of the memory and most of the
- * time. Staging, census, raw-cost WTA and the masks are computed for the whole frame by every band (their
- * neighbourhoods reach D rows across a band border for the vertical views, and the recursive median
+ * four SGM pair volumes and the final sum / WTA (sgm.cpp:26-455, hpp:283) -- most of the time and, in a context made
+ * with sister_create_band, most of the memory (a context made with sister_create keeps whole-frame volumes and merely
+ * fills the band's rows). Staging, census, raw-cost WTA and the masks are computed for the whole frame by every band
+ * (their neighbourhoods reach D rows across a band border for the vertical views, and the recursive median
  * (postprocess.cpp:15-71 in place) is a whole-map recurrence).
- * The row paths of SGM are local to a band. A column or diagonal path crosses the bands: pass 0 runs top to
- * bottom, pass 1 bottom to top, and a band continues each path from the state the neighbouring band left --
- * the exact recurrence, no approximate overlap. That state is sister_band_state_bytes() of device memory per
- * pass; moving it between the GPUs (NCCL send / recv, cudaMemcpyPeer) is the caller's job, see
+ * Every SGM path but the horizontal one crosses the bands, and the horizontal path is paired with a diagonal one
+ * (sister_b200/csrc/sgm.cu): pass 0 runs top to bottom, pass 1 bottom to top, and a band continues each path from the state
+ * the neighbouring band left -- the exact recurrence, no approximate overlap. That state is sister_band_state_bytes() of
+ * device memory per pass; moving it between the GPUs (NCCL send / recv, cudaMemcpyPeer) is the caller's job, see
  * sister_b200/bands.py for the schedule (pass 0 flows down the ranks while pass 1 flows up).
  *
- *   sister_band_submit    staging .. masks for the whole frame, fused cost and row paths for the band; mode: 0
- *                         multiview, 1 horizontal, 2 vertical (one map per call)
- *   sister_band_vertical  the column / diagonal paths of one pass inside the band. state_in_dev: what the band
- *                         above (pass 0) / below (pass 1) wrote, NULL on the first band of the pass;
- *                         state_out_dev: receives the state for the next band, NULL on the last band
+ *   sister_band_submit    staging .. masks for the whole frame, fused cost for the band; mode: 0 multiview,
+ *                         1 horizontal, 2 vertical (one map per call)
+ *   sister_band_vertical  the four paths of one pass inside the band. state_in_dev: what the band above (pass 0) /
+ *                         below (pass 1) wrote, NULL on the first band of the pass; state_out_dev: receives the state
+ *                         for the next band, NULL on the last band (SISTER_E_ARG when a state that is needed is missing)
  *   sister_band_finish    final sum + WTA + encode of the band's rows of the crop into out_dev, a full H x W
  *                         uint16 map of which only the band's rows are written
  * All three only enqueue on the slot's stream; sister_sync(slot) completes them. Outputs are bit-identical to
- * sister_compute on one GPU (tests/test_bands.py).
+ * sister_compute on one GPU (tests/test_bands_gpu.py).
  */
 size_t sister_band_state_bytes(int w, int h, int disp_count);
+/* A context for row bands only: like sister_create, but the volumes of a slot -- the fused cost and the four SGM pair
+ * volumes, 5 bytes per cell -- hold max_band_rows rows of the padded frame instead of all h + 2 * disp_count, so that a frame
+ * whose volumes do not fit one GPU can be split over several (or run band after band on one). The per-pixel buffers (images,
+ * census codes, per-view maps: about 140 bytes per padded pixel) still cover the whole frame. Such a context accepts the
+ * sister_band_* calls only (anything else: SISTER_E_CAPACITY). */
+int sister_create_band(sister_ctx **ctx, int device, int max_w, int max_h, int max_disp, int n_slots, int max_band_rows);
 int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h, int channels,
                        int disp_count, int mode, int band_row0, int band_row1);
 int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *state_in_dev, uint8_t *state_out_dev);

@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "sister_submit_device", "sister_sync", "sister_dev_alloc", "sister_dev_free", "sister_host_alloc", "sister_host_free", "sister_dev_upload",
     "sister_dev_download", "sister_set_profiling", "sister_region_begin", "sister_region_end", "sister_get_stage_ms", "sister_get_stage_launches",
     "sister_get_launch_count", "sister_debug_fetch", "sister_set_test_taps", "sister_set_full_frame",
-    "sister_stereo", "sister_band_state_bytes", "sister_band_submit", "sister_band_vertical", "sister_band_finish", "sister_test_sgm", "sister_strerror", "sister_last_error",
+    "sister_stereo", "sister_create_band", "sister_band_state_bytes", "sister_band_submit", "sister_band_vertical", "sister_band_finish", "sister_test_sgm", "sister_strerror", "sister_last_error",
     "sister_version",
 )
 
@@ -62,6 +62,8 @@ def load_library():
     vp = C.c_void_p
     L.sister_create.restype = C.c_int
     L.sister_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.sister_create_band.restype = C.c_int
+    L.sister_create_band.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.sister_destroy.argtypes = [vp]
     L.sister_compute.restype = C.c_int
     L.sister_compute.argtypes = [vp, C.POINTER(_u8p), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_uint,
@@ -151,11 +153,16 @@ def _views_ptrs_strided(views):
 class Engine:
     """One context on one GPU: ``n_slots`` rigs in flight, sized for rigs up to max_w x max_h x max_disp."""
 
-    def __init__(self, max_w: int, max_h: int, max_disp: int, n_slots: int = 1, device: int = 0):
+    def __init__(self, max_w: int, max_h: int, max_disp: int, n_slots: int = 1, device: int = 0, max_band_rows: int = 0):
+        """max_band_rows > 0: a context for row bands only (sister_create_band): the volumes hold that many rows of the
+        padded frame instead of all of them."""
         self.lib = load_library()
         self.ctx = C.c_void_p()
         self.n_slots = n_slots
-        self._chk(self.lib.sister_create(C.byref(self.ctx), device, max_w, max_h, max_disp, n_slots), create=True)
+        if max_band_rows > 0:
+            self._chk(self.lib.sister_create_band(C.byref(self.ctx), device, max_w, max_h, max_disp, n_slots, max_band_rows), create=True)
+        else:
+            self._chk(self.lib.sister_create(C.byref(self.ctx), device, max_w, max_h, max_disp, n_slots), create=True)
         self._dev_allocs = []
         self._host_allocs = []
 

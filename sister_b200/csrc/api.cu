@@ -50,6 +50,8 @@ struct sister_ctx {
     int device = 0;
     int max_w = 0, max_h = 0, max_d = 0;
     long long px_max = 0, cells_max = 0;
+    int band_rows = 0;       // > 0: a band context (sister_create_band): the volumes hold this many rows of the padded frame
+    long long vol_cells = 0; // cells a slot's fused volume (and each pair volume) holds
     size_t in_bytes_max = 0;
     std::vector<Slot> slots;
     bool profiling = false;
@@ -83,7 +85,7 @@ cudaError_t take_launch_error(sister_ctx *ctx)
     return e;
 }
 
-int check_shape(sister_ctx *ctx, int w, int h, int D, Dims &d)
+int check_shape(sister_ctx *ctx, int w, int h, int D, Dims &d, bool band_call = false)
 {
     if (w <= 0 || h <= 0 || D <= 0) { ctx->err = "non-positive size"; return SISTER_E_ARG; }
     if (D % 8 != 0) { ctx->err = "disp_count must be a multiple of 8 (sgm.cpp:268)"; return SISTER_E_SHAPE; }
@@ -97,6 +99,10 @@ int check_shape(sister_ctx *ctx, int w, int h, int D, Dims &d)
     if (d.cells / 8 > 0x7F000000LL) { ctx->err = "cost volume above 1.7e10 cells (32-bit cursor offsets in sgm.cu)"; return SISTER_E_SHAPE; }
     if (w > ctx->max_w || h > ctx->max_h || D > ctx->max_d || d.px > ctx->px_max || d.cells > ctx->cells_max) {
         ctx->err = "rig larger than the capacity given to sister_create";
+        return SISTER_E_CAPACITY;
+    }
+    if (ctx->band_rows > 0 && !band_call) {
+        ctx->err = "a band context (sister_create_band) holds a band of the volumes only: use sister_band_*";
         return SISTER_E_CAPACITY;
     }
     return SISTER_OK;
@@ -127,6 +133,7 @@ int run_pipeline(sister_ctx *ctx, Slot &s, const uint8_t *const in_views[5], int
                  unsigned mode_mask, uint16_t *const out_dev[3])
 {
     s.n_ev = 0;
+    s.sgm.row_shift = 0;
     int before[16];
     memcpy(before, ctx->lc.stage, sizeof(before));
     // the status word ACCUMULATES (kernels atomicOr into it) over every submit queued on the slot until finish_slot has
@@ -248,9 +255,9 @@ const char *sister_strerror(int code)
 
 const char *sister_last_error(sister_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-int sister_create(sister_ctx **out, int device, int max_w, int max_h, int max_disp, int n_slots)
+static int create_impl(sister_ctx **out, int device, int max_w, int max_h, int max_disp, int n_slots, int band_rows)
 {
-    if (!out || max_w <= 0 || max_h <= 0 || max_disp <= 0 || n_slots <= 0 || n_slots > 64) return SISTER_E_ARG;
+    if (!out || max_w <= 0 || max_h <= 0 || max_disp <= 0 || n_slots <= 0 || n_slots > 64 || band_rows < 0) return SISTER_E_ARG;
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SISTER_E_DEVICE;
@@ -263,12 +270,14 @@ int sister_create(sister_ctx **out, int device, int max_w, int max_h, int max_di
     ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_d = max_disp;
     ctx->px_max = (long long)(max_w + 2 * max_disp) * (max_h + 2 * max_disp);
     ctx->cells_max = ctx->px_max * max_disp;
+    ctx->band_rows = band_rows;
+    ctx->vol_cells = band_rows > 0 ? (long long)(max_w + 2 * max_disp) * band_rows * max_disp : ctx->cells_max;
     ctx->in_bytes_max = (size_t)5 * max_w * max_h * 3;
     int rc = SISTER_OK;
     auto bail = [&](int code) { for (auto &s : ctx->slots) free_slot(s); delete ctx; return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(SISTER_E_DEVICE);
     ctx->slots.resize(n_slots);
-    const size_t px = (size_t)ctx->px_max, cells = (size_t)ctx->cells_max, wh = (size_t)max_w * max_h;
+    const size_t px = (size_t)ctx->px_max, wh = (size_t)max_w * max_h;
     for (auto &s : ctx->slots) {
         cudaError_t e = cudaSuccess;
         auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
@@ -278,8 +287,10 @@ int sister_create(sister_ctx **out, int device, int max_w, int max_h, int max_di
         A((void **)&s.d_oriented, 8 * px); A((void **)&s.d_census, 8 * px * 8);
         A((void **)&s.d_wtaL, 4 * px * 2); A((void **)&s.d_wtaR, 4 * px * 2);
         A((void **)&s.d_medL, 4 * px * 2); A((void **)&s.d_medR, 4 * px * 2); A((void **)&s.d_lr, 4 * px * 2);
-        A((void **)&s.d_masks, 4 * px); A((void **)&s.d_fused, cells); A((void **)&s.sgm.vols, 4 * cells);
-        s.sgm.mailbox_bytes = sgm_mailbox_bytes(max_w, max_h, max_disp);
+        const size_t vol = (size_t)ctx->vol_cells;
+        A((void **)&s.d_masks, 4 * px); A((void **)&s.d_fused, vol); A((void **)&s.sgm.vols, 4 * vol);
+        s.sgm.vol_stride = band_rows > 0 ? vol : 0;
+        s.sgm.mailbox_bytes = sgm_mailbox_bytes(max_w, max_h, max_disp, band_rows);
         A((void **)&s.sgm.mailbox, s.sgm.mailbox_bytes);
         A((void **)&s.d_raw, 3 * px * 2); A((void **)&s.d_out, 3 * wh * 2); H((void **)&s.h_out, 3 * wh * 2);
         A((void **)&s.d_status, sizeof(int)); H((void **)&s.h_status, sizeof(int));
@@ -292,6 +303,17 @@ int sister_create(sister_ctx **out, int device, int max_w, int max_h, int max_di
     cudaDeviceSynchronize();
     *out = ctx;
     return SISTER_OK;
+}
+
+int sister_create(sister_ctx **out, int device, int max_w, int max_h, int max_disp, int n_slots)
+{
+    return create_impl(out, device, max_w, max_h, max_disp, n_slots, 0);
+}
+
+int sister_create_band(sister_ctx **out, int device, int max_w, int max_h, int max_disp, int n_slots, int max_band_rows)
+{
+    if (max_band_rows <= 0) return SISTER_E_ARG;
+    return create_impl(out, device, max_w, max_h, max_disp, n_slots, max_band_rows);
 }
 
 int sister_destroy(sister_ctx *ctx)
@@ -442,9 +464,10 @@ int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev
     if (rc) return rc;
     if (!views_dev || (channels != 1 && channels != 3) || mode < 0 || mode > 2) { ctx->err = "bad views/channels/mode"; return SISTER_E_ARG; }
     Dims d;
-    rc = check_shape(ctx, w, h, disp_count, d);
+    rc = check_shape(ctx, w, h, disp_count, d, true);
     if (rc) return rc;
     if (band_row0 < 0 || band_row1 > d.Hp || band_row0 >= band_row1) { ctx->err = "band rows must satisfy 0 <= row0 < row1 <= h + 2 * disp_count"; return SISTER_E_ARG; }
+    if (ctx->band_rows > 0 && band_row1 - band_row0 > ctx->band_rows) { ctx->err = "band taller than the max_band_rows given to sister_create_band"; return SISTER_E_CAPACITY; }
     Slot &s = ctx->slots[slot];
     SCK(cudaSetDevice(ctx->device));
     if (s.busy && s.host_io) { ctx->err = "slot has an un-waited host submit"; return SISTER_E_BUSY; }
@@ -460,7 +483,10 @@ int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev
     launch_census(s.d_oriented, d, s.d_census, s.st, ctx->lc);
     launch_match_wta(s.d_census, d, vm, s.d_wtaL, s.d_wtaR, s.st, ctx->lc);
     launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, vm, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.st, ctx->lc);
-    launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused, s.d_status, s.st, ctx->lc, band_row0, band_row1);
+    // a band context's volumes start with the band's first row: every kernel addresses rows of the padded frame, so the
+    // bases are moved back by the rows that are not there (only the band's rows are ever touched)
+    s.sgm.row_shift = ctx->band_rows > 0 ? (size_t)band_row0 * (size_t)d.Wp * (size_t)d.D : 0;
+    launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused - s.sgm.row_shift, s.d_status, s.st, ctx->lc, band_row0, band_row1);
     s.last_fused = s.d_fused;
     SCK(cudaGetLastError());
     SCK(take_launch_error(ctx));
@@ -484,7 +510,7 @@ int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *sta
     const bool last_of_pass = pass == 0 ? s.band_r1 == s.dims.Hp : s.band_r0 == 0;
     if (!first_of_pass && !state_in_dev) { ctx->err = "state_in_dev is NULL but the band is not the first of this pass"; return SISTER_E_ARG; }
     if (!last_of_pass && !state_out_dev) { ctx->err = "state_out_dev is NULL but the band is not the last of this pass"; return SISTER_E_ARG; }
-    launch_sgm_band(1 + pass, s.d_fused, s.dims, s.band_r0, s.band_r1, state_in_dev, state_out_dev, s.sgm, nullptr, nullptr, s.d_status, s.st, ctx->lc);
+    launch_sgm_band(1 + pass, s.d_fused - s.sgm.row_shift, s.dims, s.band_r0, s.band_r1, state_in_dev, state_out_dev, s.sgm, nullptr, nullptr, s.d_status, s.st, ctx->lc);
     SCK(cudaGetLastError());
     SCK(take_launch_error(ctx));
     return SISTER_OK;
@@ -497,7 +523,7 @@ int sister_band_finish(sister_ctx *ctx, int slot, uint16_t *out_dev)
     Slot &s = ctx->slots[slot];
     if (!out_dev || s.band_r1 <= s.band_r0) { ctx->err = "sister_band_submit first; out_dev must not be null"; return SISTER_E_ARG; }
     SCK(cudaSetDevice(ctx->device));
-    launch_sgm_band(3, s.d_fused, s.dims, s.band_r0, s.band_r1, nullptr, nullptr, s.sgm, nullptr, out_dev, s.d_status, s.st, ctx->lc);
+    launch_sgm_band(3, s.d_fused - s.sgm.row_shift, s.dims, s.band_r0, s.band_r1, nullptr, nullptr, s.sgm, nullptr, out_dev, s.d_status, s.st, ctx->lc);
     SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
     SCK(cudaGetLastError());
     s.band_r0 = s.band_r1 = 0; // sister_sync(slot) completes the band and checks the status word

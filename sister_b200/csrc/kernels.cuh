@@ -63,13 +63,15 @@ void launch_fuse(const unsigned long long *census, const uint8_t *masks, const D
 // sweep hand the rider states on (sgm_mailbox_bytes), with the epoch of its tags.
 struct SgmScratch {
     uint8_t *vols = nullptr;
+    size_t vol_stride = 0;  // bytes between two pair volumes (0: d.cells, the whole frame)
+    size_t row_shift = 0;   // a band context holds the rows from band_row0 on only: band_row0 * Wp * D, subtracted from the bases
     uint8_t *mailbox = nullptr;
     size_t mailbox_bytes = 0;
     unsigned epoch = 0;
     unsigned long long geo_key = 0;
 };
 // mailbox size that serves every rig a context of this capacity accepts
-size_t sgm_mailbox_bytes(int max_w, int max_h, int max_d);
+size_t sgm_mailbox_bytes(int max_w, int max_h, int max_d, int band_rows = 0);
 // 8-path SGM (sgm.cpp:26-455) on the uint8 fused volume: four two-path sweeps write four one-byte pair volumes, then
 // S = nC * C + sum of the pair bytes, the final WTA-left (hpp:283) and convertTo/crop/*255 (hpp:111-118) in one sweep.
 // sum (uint16 [Hp][Wp][D]) is written only when non-null (test tap); raw_disp / out may be null.

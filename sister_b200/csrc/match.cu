@@ -413,7 +413,7 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
 template <int T, int NK, int ORDER, bool TRIPLE> // NK = D / 32 when D is a multiple of 32 (fully unrolled), 0 = any D
 __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__restrict__ census, const uint8_t *__restrict__ masks,
                                                  Dims d, unsigned view_mask, uint8_t *__restrict__ fused, uint8_t *__restrict__ fused_h,
-                                                 uint8_t *__restrict__ fused_v, int *__restrict__ status, int row_lo)
+                                                 uint8_t *__restrict__ fused_v, int *__restrict__ status, int row_lo, int row_hi)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned s_any;
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(32 * T) k_fuse(const unsigned long long *__res
     __syncthreads();
     const int lane = tid & 31, li = tid >> 5;
     const int i = i0 + li;
-    if (i >= d.Hp) return;
+    if (i >= row_hi) return; // (row_hi <= Hp; a band's volumes end with its last row)
     constexpr int NKC = NK > 0 ? NK : 16;
     bool overflow = false;
     // The lane writes bytes lane + 32k of the cell; which disparity that is depends on the cell's byte order (Dims,
@@ -670,11 +670,11 @@ static void launch_fuse_o(const unsigned long long *census, const uint8_t *masks
     dim3 grid((d.Wp + T - 1) / T, (row_hi - row_lo + T - 1) / T);
     if (fused_h && fused_v) {
         lc.fail(optin_dynamic_smem((const void *)k_fuse<T, NK, ORDER, true>, smem));
-        k_fuse<T, NK, ORDER, true><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, fused_h, fused_v, status, row_lo);
+        k_fuse<T, NK, ORDER, true><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, fused_h, fused_v, status, row_lo, row_hi);
         return;
     }
     lc.fail(optin_dynamic_smem((const void *)k_fuse<T, NK, ORDER, false>, smem));
-    k_fuse<T, NK, ORDER, false><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, nullptr, nullptr, status, row_lo);
+    k_fuse<T, NK, ORDER, false><<<grid, 32 * T, smem, st>>>(census, masks, d, view_mask, fused, nullptr, nullptr, status, row_lo, row_hi);
 }
 
 template <int T, int NK>

@@ -24,8 +24,7 @@
 //     state stays in its chain's registers. The rider's state is handed from chain n-1 to chain n between steps: what chain
 //     n-1 left after step t-1 IS the diagonal predecessor of chain n at step t. The hand-over is one-directional, so the
 //     blocks of a sweep form a pipeline (block b consumes what block b-1 published), never a two-sided wavefront:
-//         inside a block    through rings of exchange entries in shared memory guarded by full / empty mbarriers between
-//                           neighbouring warps: warps run free, each just behind the one in front (no block barrier);
+//         inside a block    through shared memory, double-buffered, one block barrier per step;
 //         between blocks    through a full-length mailbox in global memory (one entry per step; every 32-bit word carries
 //                           the launch's 4-bit epoch tag in the top bits of its bytes -- states are <= P2 < 128 -- so a word
 //                           is valid or not by itself: no flags, no fences, no ring, no back-pressure, and a block that is
@@ -37,6 +36,7 @@
 // Traffic per cell of the region: 4 x (1 B read C + 1 B write) + (1 + 4) B read = 13 B (round 1: 25 B with eight
 // independent-chain path volumes).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -47,10 +47,10 @@ namespace sister {
 
 // compute warps per block (+ 1 mailbox warp): up to 18 while a lane holds few registers of state, fewer for the long
 // disparity ranges, whose state needs the registers a smaller block leaves per thread
-__host__ __device__ constexpr int sweep_warps_max(int NR) { return NR <= 8 ? 18 : NR <= 12 ? 12 : 8; }
+__host__ __device__ constexpr int sweep_warps_max(int NR) { return NR <= 8 ? 20 : NR <= 12 ? 12 : 8; }
 constexpr int kSweepWarpsMin = 6;  // the mailbox allocation of a context is sized for this many (sgm_mailbox_bytes)
 constexpr int kRing = 8;           // cost ring slots per warp
-constexpr int kSpinLimit = 1 << 21;
+constexpr unsigned long long kWaitNs = 4000000000ull; // a hand-over that takes 4 s is a broken pipeline, not a slow one
 
 // Region of interest: the cells whose aggregated cost is consumed. The caller only ever sees the crop
 // Rect(D, D, W, H) of the disparity map (hpp:116-118), so outside of test / raw-disparity runs the pair bytes are
@@ -71,6 +71,7 @@ struct SweepGeo {
     int base8, sn8, st8; // cell of (chain 0, step 0), increment per chain, increment per step
     int row;           // 1: row sweep (first line: chain 0; rider off the image: step 0); 0: column sweep (the reverse)
     int lead;          // dead slots in front of chain n0 (a row sweep that starts on the first line keeps that chain alone in its warp)
+    int nw;            // compute warps per block of this sweep
     int nblk;          // blocks
     int vol;           // pair volume
     long long mb_off;  // first mailbox entry; block b publishes entries [mb_off + b * (t1 - t0), + (t1 - t0))
@@ -81,11 +82,23 @@ struct SweepGeo {
 struct SweepPlan {
     SweepGeo g[4];
     int lvl_vid[5], lvl_pos[4], lvl_n[4], lvl_sweep[4][4]; // block id -> (sweep, block of the sweep): round-robin over the sweeps
-    int nw;            // compute warps per block
+    int nw_max;        // the largest of the sweeps' compute warps per block: the mailbox warp is warp nw_max
     int total_blocks;
+    long long vol_stride; // bytes between two pair volumes
     unsigned tagword;  // the launch's epoch in bit 7 of each byte
     long long entries; // mailbox entries used
 };
+
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#ifdef SISTER_DEBUG_HOOKS
+// measurement aid: per block {start ns, end ns, SM, sweep * 65536 + block of the sweep} of the last sweep launch
+__device__ unsigned long long g_sweep_times[2048][4];
+__device__ __forceinline__ unsigned sm_id() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+extern "C" int sister_debug_sweep_times(void *host, size_t bytes)
+{
+    return (int)cudaMemcpyFromSymbol(host, g_sweep_times, bytes < sizeof(g_sweep_times) ? bytes : sizeof(g_sweep_times));
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------- small device helpers
 
@@ -99,7 +112,15 @@ __device__ __forceinline__ uint4 lds128v(unsigned a) { uint4 v; asm volatile("ld
 __device__ __forceinline__ void sts64(unsigned a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};\n" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 __device__ __forceinline__ uint32_t ld_relaxed(const uint8_t *p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_relaxed(uint8_t *p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
+// The step barrier of a block (compute warps + mailbox warp; warps without a role have left). Warps of different roles reach
+// it from different places of the code, which bar.sync permits (every warp executes it as a whole) but compute-sanitizer's
+// synccheck reports as "divergent threads in block"; -DSISTER_ONE_BARRIER_INSTRUCTION routes every role through one
+// out-of-line instance for that tool (profiles/r02_sanitize_synccheck.txt) -- at the cost of a call per step, so not by default.
+#ifdef SISTER_ONE_BARRIER_INSTRUCTION
+__device__ __noinline__ void block_sync(int n_threads) { asm volatile("bar.sync 1, %0;\n" ::"r"(n_threads) : "memory"); }
+#else
 __device__ __forceinline__ void block_sync(int n_threads) { asm volatile("bar.sync 1, %0;\n" ::"r"(n_threads) : "memory"); }
+#endif
 
 // the lane's NR / 2 words of its chain's cell in a ring slot (a = slot + the chain's cell + the lane's first byte)
 template <int NR, int LPC, bool FULL, bool IL> __device__ __forceinline__ void ring_read(unsigned a, int valid_bytes, uint32_t (&w)[NR / 2])
@@ -137,24 +158,22 @@ template <int NR> __device__ __forceinline__ void state_to_words(const uint32_t 
 #pragma unroll
     for (int k = 0; k < NR / 2; k++) w[k] = ((a[2 * k + 1] * 256u + a[2 * k]) & 0x7F7F7F7Fu) | tag; // pads (disparities >= D) are dropped
 }
-// `off` (0 or the phase offset of the exchange ring, below) is added to the disparities' halves before the padding halves
-// are set to their constant
-template <int NR, int LPC, bool FULL> __device__ __forceinline__ void words_to_state(const uint32_t (&w)[NR / 2], const LaneInfo<NR, LPC, FULL> &li, uint32_t (&a)[NR], uint32_t off = 0u)
+template <int NR, int LPC, bool FULL> __device__ __forceinline__ void words_to_state(const uint32_t (&w)[NR / 2], const LaneInfo<NR, LPC, FULL> &li, uint32_t (&a)[NR])
 {
 #pragma unroll
     for (int k = 0; k < NR / 2; k++) {
         const uint32_t x = w[k] & 0x7F7F7F7Fu;
-        a[2 * k + 1] = li.padded(__byte_perm(x, 0u, 0x4341) + off, 2 * k + 1);
-        a[2 * k] = li.padded((x & 0x00FF00FFu) + off, 2 * k);
+        a[2 * k + 1] = li.padded(__byte_perm(x, 0u, 0x4341), 2 * k + 1);
+        a[2 * k] = li.padded(x & 0x00FF00FFu, 2 * k);
     }
 }
 // plain (untagged) entry in global memory: a band state
-template <int NR, int LPC, bool FULL> __device__ __forceinline__ void entry_load(const uint8_t *entry, const LaneInfo<NR, LPC, FULL> &li, uint32_t (&a)[NR], uint32_t off = 0u)
+template <int NR, int LPC, bool FULL> __device__ __forceinline__ void entry_load(const uint8_t *entry, const LaneInfo<NR, LPC, FULL> &li, uint32_t (&a)[NR])
 {
     uint32_t w[NR / 2];
 #pragma unroll
     for (int k = 0; k < NR / 2; k++) w[k] = __ldg(reinterpret_cast<const uint32_t *>(entry) + k * LPC + li.sl);
-    words_to_state<NR, LPC, FULL>(w, li, a, off);
+    words_to_state<NR, LPC, FULL>(w, li, a);
 }
 template <int NR, int LPC, bool FULL> __device__ __forceinline__ void entry_store(uint8_t *entry, const LaneInfo<NR, LPC, FULL> &li, const uint32_t (&a)[NR])
 {
@@ -184,46 +203,13 @@ __device__ __forceinline__ void rider_step(const uint32_t (&a)[NR], const uint32
     for (int k = 0; k < NR; k++) out[k] = li.padded(__viaddmin_s16x2(L[k], neg2, kP2x2), k);
 }
 
-// ---- hand-over between the warps of a block: a ring of kXR exchange entries per chain boundary, guarded by one "full" and
-// one "empty" mbarrier per entry of every boundary that separates two warps (chains of one warp are in lock step).
-//   writer (the warp in front), step s:   wait empty[s % kXR] (lap s / kXR) -- write the state it leaves -- arrive full[s % kXR]
-//   reader (the warp behind), step s + 1: wait full[s % kXR]  (lap s / kXR) -- read                       -- arrive empty[s % kXR]
-// Warps run free, each as far behind the one in front as the hand-over takes, never more than kXR - 1 steps ahead of the
-// one behind. The waits are hardware suspends (mbarrier.try_wait), not polls: a waiting warp takes no issue slot.
-constexpr int kXR = 4;       // entries per boundary = steps per trip of the step loop
-
-__device__ __forceinline__ void mbar_init(unsigned bar_s, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar_s), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(unsigned bar_s) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_s) : "memory"); }
-// Wait for the phase of parity `parity`. The loop is bounded (a broken pipeline must never hang the device): try_wait
-// suspends the warp in hardware for up to the time hint, so the rounds are few and cost no issue slots while waiting.
-__device__ __forceinline__ bool mbar_wait(unsigned bar_s, unsigned parity, bool &broken)
-{
-    unsigned ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\tmov.u32 n, 0;\n\t"
-        "MBW_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t@p bra MBW_DONE;\n\t"
-        "add.u32 n, n, 1;\n\tsetp.lt.u32 p, n, 4096;\n\t@p bra MBW_LOOP;\n\t"
-        "mov.u32 %0, 0;\n\tbra MBW_END;\n\tMBW_DONE:\n\tmov.u32 %0, 1;\n\tMBW_END:\n\t}\n"
-        : "=r"(ok) : "r"(bar_s), "r"(parity) : "memory");
-    if (!ok) broken = true;
-    return ok != 0u;
-}
-// every lane arrives (the barriers count 32 arrivals): no election, no warp synchronisation, and each lane's own writes are
-// released by its own arrival
-__device__ __forceinline__ void warp_arrive(unsigned bar_s, int lane) { (void)lane; mbar_arrive(bar_s); }
-// barriers of warp boundary wb: full[0 .. kXR), empty[0 .. kXR), 8 bytes each
-__device__ __forceinline__ unsigned bar_full(unsigned bars_s, int wb, int e) { return bars_s + (unsigned)((wb * 2 * kXR + e) * 8); }
-__device__ __forceinline__ unsigned bar_empty(unsigned bars_s, int wb, int e) { return bars_s + (unsigned)((wb * 2 * kXR + kXR + e) * 8); }
-
 // ---------------------------------------------------------------------------------------------- the sweep kernel
 
 // MODE 0: carrier + rider; 1: rider only (chains in front of the region); 2: the warp that holds the first line of a row
-// sweep (carrier = the literal first-line arithmetic, rider restarts from the zero state at every step, nothing is read)
-// in_wb / out_wb: the warp boundaries this warp reads from / writes to (-1: nobody on the other side)
+// sweep (carrier = the literal first-line arithmetic, rider restarts from the zero state at every step)
 template <int NR, int LPC, bool FULL, bool IL, int MODE>
 __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, uint8_t *__restrict__ vol, const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, int D,
-                                           int n, bool alive, bool car, int cl, unsigned ring_s, unsigned x_s, unsigned bars_s, int in_wb, int out_wb, int lane,
-                                           int n_sync, int *__restrict__ status)
+                                           int n, bool alive, bool car, int cl, unsigned ring_s, unsigned x_s, int x_stride, int lane, int n_sync)
 {
     constexpr int CPW = 32 / LPC;
     constexpr int DS = 2 * NR * LPC;          // bytes of a cell in a ring slot (>= D), of a mailbox / band entry
@@ -232,11 +218,9 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
     constexpr int SS = CPW * DS;              // bytes per ring slot
     constexpr int R = kRing, A = R - 1, U = R / 2;
     constexpr int EX = NR * LPC * 4;          // bytes of an exchange entry
-    static_assert(U == kXR, "a trip of the step loop is one lap of the exchange ring");
     const int T = g.t1 - g.t0;
     const int sub = lane / LPC;
     const int valid_bytes = li.valid_bytes(D);
-    const int ts_lo = g.ts0 - g.t0, ts_n = g.ts1 - g.ts0; // steps (relative to the first) whose cells are stored
     // ---- cost ring: chunk gch = lane + 32 m of a warp step belongs to the cell of sub-chain gch / chunks-per-cell
     const int cpc = FULL ? DS / CB : D / CB;
     const uint8_t *cp_src[NCP];
@@ -270,9 +254,8 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
     for (int s = 0; s < A; s++) copy_step(s < T, s * SS);
     const unsigned rd_lane = ring_s + sub * DS + li.template cell_offset<IL>();
     unsigned half = 0, other = U * SS;
-    unsigned lap = 0u; // parity of the exchange ring's lap = of the trip
     auto wr_off = [&](const int u) { return u == 0 ? other + (U - 1) * SS : half + (u - 1) * SS; };
-    auto next_trip = [&]() { const unsigned t = half; half = other; other = t; lap ^= 1u; };
+    auto next_trip = [&]() { const unsigned t = half; half = other; other = t; };
     // ---- state
     ChainState<NR> cs;
     uint32_t mm = 0; // MODE 2: minimum of the truncated first-line state
@@ -280,52 +263,34 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
     uint32_t rider_out[NR];
 #pragma unroll
     for (int k = 0; k < NR; k++) rider_out[k] = 0u;
-    const unsigned x_in = x_s + (unsigned)cl * (kXR * EX), x_out = x_in + kXR * EX; // + entry * EX
+    const unsigned x_in = x_s + (unsigned)cl * EX, x_out = x_in + EX; // + parity * x_stride
     const bool frame_start = g.t0 == 0;
+    const int ts_lo = g.ts0 - g.t0, ts_n = g.ts1 - g.ts0; // steps (relative to the first) whose cells are stored
     const long long band_chain = (long long)(n - g.n0) * DS, band_riders = (long long)(g.n1 - g.n0) * DS;
     if (!g.row && g.band_in) { // a column sweep continued from the band before: [carrier states | rider states] per chain
         uint32_t a[NR];
         entry_load<NR, LPC, FULL>(g.band_in + band_chain, li, a);
         chain_resume<NR, LPC, FULL>(cs, a, li);
-        // what this chain left after the step before the band: the entry before entry 0
         entry_load<NR, LPC, FULL>(g.band_in + band_riders + band_chain, li, rider_out);
-        xch_write<NR, LPC>(x_out + (kXR - 1) * EX, li.sl, rider_out);
+        xch_write<NR, LPC>(x_out, li.sl, rider_out); // what this chain left after the step before the band: parity 0 = first step of the band
     }
     uint8_t *dst = vol + (long long)my_off8 * 8 + li.template cell_offset<IL>();
-    const unsigned in_full = in_wb >= 0 ? bar_full(bars_s, in_wb, 0) : 0u, in_empty = in_wb >= 0 ? bar_empty(bars_s, in_wb, 0) : 0u;
-    const unsigned out_full = out_wb >= 0 ? bar_full(bars_s, out_wb, 0) : 0u, out_empty = out_wb >= 0 ? bar_empty(bars_s, out_wb, 0) : 0u;
-    block_sync(n_sync); // the barriers are initialised, the entries of the first step (band states) are in place
-    bool broken = false;
-    // GEN: the general step (first trip, trips that straddle an edge of the stored range, tail); otherwise STORE says whether
-    // the whole trip lies inside the stored range, and nothing is tested
+    block_sync(n_sync); // the exchange entries of the first step (helper: predecessor block / constants; above: band states) are in place
+    // GEN: the general step (first trip, trips that straddle an edge of the stored range, the last trips); otherwise STORE
+    // says whether the whole trip lies inside the stored range, and nothing is tested
     auto step = [&](const int s, const int u, auto gen_tag, auto store_tag) {
         constexpr bool GEN = decltype(gen_tag)::value, STORE = decltype(store_tag)::value;
-        constexpr int kPrev = kXR - 1;
-        uint32_t c[NR], q1[NR];
-        // ---- the rider's state: what the neighbouring chain left after step s - 1 (entry (s - 1) mod kXR; lap of step s - 1)
-        uint32_t ra[NR];
-        const int e_in = (u + kPrev) % kXR;
-        if (MODE == 2 || (GEN && frame_start && s == 0)) {
-            // first line: zero state; row sweep at its first column: the predecessor is off the image
-            const uint32_t v = (MODE != 2 && g.row) ? kP2x2 : 0u;
+        uint32_t c[NR], q1[NR], ra[NR];
+        // ---- the rider's state: what the neighbouring chain left after the previous step
+        if constexpr (MODE == 2) {
 #pragma unroll
-            for (int k = 0; k < NR; k++) ra[k] = li.padded(v, k);
-            if (GEN && MODE != 2 && s == 0 && in_wb >= 0) { // nothing to read at the first step: every entry starts out free
-#pragma unroll
-                for (int e = 0; e < kXR; e++) mbar_arrive(in_empty + 8u * e);
-            }
+            for (int k = 0; k < NR; k++) ra[k] = li.padded(0u, k);
         } else {
-            if (in_wb >= 0 && (!GEN || s > 0)) {
-                if (!mbar_wait(in_full + 8u * e_in, u == 0 ? lap ^ 1u : lap, broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
-            }
-            xch_read<NR, LPC>(x_in + e_in * EX, li.sl, ra);
-            if (in_wb >= 0) {
-                if (GEN && s == 0) { // a band's first step read the entry before entry 0; the others start out free
+            xch_read<NR, LPC>(x_in + ((u & 1) ? (unsigned)x_stride : 0u), li.sl, ra);
+            if (GEN && frame_start && s == 0) { // row sweep: the predecessor column is off the image; column sweep: first line
+                const uint32_t v = g.row ? kP2x2 : 0u;
 #pragma unroll
-                    for (int e = 0; e < kXR; e++) mbar_arrive(in_empty + 8u * e);
-                } else {
-                    mbar_arrive(in_empty + 8u * e_in);
-                }
+                for (int k = 0; k < NR; k++) ra[k] = li.padded(v, k);
             }
         }
         {
@@ -342,12 +307,9 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
             unpack_cost<NR, IL>(w, c);
         }
         copy_step(!GEN || s + A < T, wr_off(u));
+        // ---- rider
         rider_step<NR, LPC, FULL>(ra, c, li, q1, rider_out);
-        if (out_wb >= 0) {
-            if (!mbar_wait(out_empty + 8u * u, lap, broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
-        }
-        xch_write<NR, LPC>(x_out + u * EX, li.sl, rider_out);
-        if (out_wb >= 0) warp_arrive(out_full + 8u * u, lane);
+        xch_write<NR, LPC>(x_out + ((u & 1) ? 0u : (unsigned)x_stride), li.sl, rider_out);
         // ---- carrier, sum, store
         if constexpr (MODE != 1) {
             uint32_t q0[NR];
@@ -360,16 +322,18 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
             }
             dst += step_bytes;
         }
+        block_sync(n_sync);
     };
     const bool all_car = __all_sync(kFull, car);
     int s0 = 0;
 #pragma unroll 1
     while (s0 + U <= T) {
+        const bool fast = s0 > 0 && s0 + U + A <= T;
         const bool inside = s0 >= ts_lo && s0 + U <= ts_lo + ts_n, outside = s0 + U <= ts_lo || s0 >= ts_lo + ts_n;
-        if (s0 > 0 && s0 + U + A <= T && inside && (all_car || MODE == 1)) {
+        if (fast && MODE == 0 && inside && all_car) {
 #pragma unroll
             for (int u = 0; u < U; u++) step(s0 + u, u, std::false_type{}, std::true_type{});
-        } else if (s0 > 0 && s0 + U + A <= T && (outside || MODE == 1)) {
+        } else if (fast && (MODE == 1 || (MODE == 0 && outside))) {
 #pragma unroll
             for (int u = 0; u < U; u++) step(s0 + u, u, std::false_type{}, std::false_type{});
         } else {
@@ -389,39 +353,47 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
     }
 }
 
-// The import warp of a block: brings the rider states of the predecessor block's last chain (or of the band before, or the
-// constant P2 of the border column) into boundary 0 of the exchange ring, one entry per step, reading the mailbox two
-// entries ahead so that the L2 round trip stays off the consumers' path.
+// The mailbox warp of a block: lanes [0, LPC) bring the predecessor block's rider state for the NEXT step into exchange
+// entry 0, lanes [LPC, 2 LPC) publish what the block's last chain left after the PREVIOUS step; both meet the compute warps
+// at the step's barrier. Entries are read two steps ahead so that the L2 round trip is off the step's critical path.
 template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ void import_warp(const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, int b, int ch, const uint8_t *__restrict__ mailbox, unsigned tagword,
-                                            unsigned x_s, unsigned bars_s, int lane, int n_sync, int *__restrict__ status)
+__device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, int b, int ch, int last_e, uint8_t *__restrict__ mailbox, unsigned tagword,
+                                             unsigned x_s, int x_stride, int lane, int n_sync, int *__restrict__ status)
 {
     constexpr int NH = NR / 2;
     constexpr int EX = NR * LPC * 4;
     constexpr long long EB = 2 * NR * LPC; // bytes of a mailbox / band entry
     const int T = g.t1 - g.t0;
-    const bool on = lane < LPC;
+    const bool imp = lane < LPC, exp = lane >= LPC && lane < 2 * LPC;
+    // where the predecessor's states come from, where the last chain's states go
     const uint8_t *src = nullptr;
     unsigned src_tag = 0u, src_mask = 0u;
     if (b > 0) { src = mailbox + (g.mb_off + (long long)(b - 1) * T) * EB; src_tag = tagword; src_mask = 0x80808080u; }
     else if (g.row && g.band_in) src = g.band_in; // the band before left one state per step, untagged
+    uint8_t *dst = nullptr;
+    unsigned dst_tag = 0u;
+    if (b < g.nblk - 1) { dst = mailbox + (g.mb_off + (long long)b * T) * EB; dst_tag = tagword; }
+    else if (g.row && g.band_out) dst = g.band_out;
     const long long lane_off = (long long)li.sl * 4;
     uint32_t a[NR];
-    if (on && !g.row && g.band_in) {
-        // a column sweep continued from the band before: the state the predecessor of the block's first chain left (the
-        // border column has none: P2) goes into the entry before entry 0
-        if (b > 0) entry_load<NR, LPC, FULL>(g.band_in + ((long long)(g.n1 - g.n0) + (long long)b * ch - 1) * EB, li, a);
-        else {
+    // entry 0 at the first step. A column sweep continued from the band before takes the predecessor of the block's first
+    // chain from the band state. With no predecessor at all (column sweep: the border column, rider = P2 for good; row sweep:
+    // the first line, whose warp ignores the entry) the constant goes into both parities once.
+    if (imp) {
+        if (!g.row && g.band_in && b > 0) {
+            const long long pred = (long long)b * ch - 1; // chain before the block's first (column sweeps have no lead)
+            entry_load<NR, LPC, FULL>(g.band_in + ((long long)(g.n1 - g.n0) + pred) * EB, li, a);
+            xch_write<NR, LPC>(x_s, li.sl, a);
+        } else if (!src) {
 #pragma unroll
             for (int k = 0; k < NR; k++) a[k] = li.padded(kP2x2, k);
+            xch_write<NR, LPC>(x_s, li.sl, a);
+            xch_write<NR, LPC>(x_s + x_stride, li.sl, a);
         }
-        xch_write<NR, LPC>(x_s + (kXR - 1) * EX, li.sl, a);
     }
-    block_sync(n_sync);
-    const unsigned full0 = bar_full(bars_s, 0, 0), empty0 = bar_empty(bars_s, 0, 0);
     uint32_t pf0[NH], pf1[NH];
     auto fetch = [&](const int s, uint32_t (&w)[NH]) { // entry s of the source: the predecessor's state after step s
-        if (on && src && s < T - 1) {
+        if (imp && src && s < T - 1) {
             const uint8_t *e = src + (long long)s * EB + lane_off;
 #pragma unroll
             for (int k = 0; k < NH; k++) w[k] = ld_relaxed(e + (long long)k * LPC * 4);
@@ -432,80 +404,70 @@ __device__ __forceinline__ void import_warp(const LaneInfo<NR, LPC, FULL> &li, c
     };
     fetch(0, pf0);
     fetch(1, pf1);
-    int spins = 0;
-    bool broken = false;
+    block_sync(n_sync);
+    const unsigned x_last = x_s + (unsigned)last_e * EX;
+    unsigned long long t_wait = 0;
 #pragma unroll 1
-    for (int s = 0; s < T - 1; s++) {
+    for (int s = 0; s < T; s++) {
+        int spins = 0;
+        // ---- publish the state the last chain left after step s - 1
+        if (exp && dst && s > 0) {
+            xch_read<NR, LPC>(x_last + ((s & 1) ? x_stride : 0), li.sl, a);
+            uint32_t w[NH];
+            state_to_words<NR>(a, dst_tag, w);
+            uint8_t *e = dst + (long long)(s - 1) * EB + lane_off;
+#pragma unroll
+            for (int k = 0; k < NH; k++) st_relaxed(e + (long long)k * LPC * 4, w[k]);
+        }
+        // ---- deliver the predecessor's state after step s for step s + 1 (read two entries ahead)
         uint32_t w[NH];
 #pragma unroll
         for (int k = 0; k < NH; k++) { w[k] = pf0[k]; pf0[k] = pf1[k]; }
         fetch(s + 2, pf1);
-        if (src) { // warp-uniform
+        if (src && s < T - 1) { // warp-uniform
             for (;;) {
                 uint32_t bad = 0u;
 #pragma unroll
                 for (int k = 0; k < NH; k++) bad |= (w[k] ^ src_tag) & src_mask;
-                if (!__any_sync(kFull, on && bad != 0u)) break;
-                if (++spins > kSpinLimit) { // never hang the device: report and carry on with what is there
+                if (!__any_sync(kFull, imp && bad != 0u)) break;
+                // bounded by time, not polls (a predecessor may be queued behind other kernels, or a tool may slow everything
+                // down): a broken pipeline must never hang the device -- report it and carry on with what is there
+                if (spins++ == 0) t_wait = global_ns();
+                else if ((spins & 255) == 0 && global_ns() - t_wait > kWaitNs) {
                     if (lane == 0) atomicOr(status, kStatusSpinTimeout);
                     src_mask = 0u;
                     break;
                 }
-                __nanosleep(20);
-                if (on) {
+                __nanosleep(32);
+                if (imp) {
                     const uint8_t *e = src + (long long)s * EB + lane_off;
 #pragma unroll
                     for (int k = 0; k < NH; k++) w[k] = ld_relaxed(e + (long long)k * LPC * 4);
                 }
             }
-            words_to_state<NR, LPC, FULL>(w, li, a);
-        } else {
-#pragma unroll
-            for (int k = 0; k < NR; k++) a[k] = li.padded(kP2x2, k); // the border column of a column sweep
+            if (imp) {
+                words_to_state<NR, LPC, FULL>(w, li, a);
+                xch_write<NR, LPC>(x_s + ((s & 1) ? 0 : x_stride), li.sl, a);
+            }
         }
-        if (!mbar_wait(empty0 + 8u * (s % kXR), (unsigned)((s / kXR) & 1), broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
-        if (on) xch_write<NR, LPC>(x_s + (s % kXR) * EX, li.sl, a);
-        warp_arrive(full0 + 8u * (s % kXR), lane);
+        block_sync(n_sync);
     }
-}
-
-// The export warp of a block: publishes the rider states the block's last chain leaves, one mailbox (or band) entry per step.
-template <int NR, int LPC, bool FULL>
-__device__ __forceinline__ void export_warp(const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, uint8_t *__restrict__ dst, unsigned dst_tag, unsigned x_last,
-                                            unsigned bars_s, int wb, int lane, int n_sync, int *__restrict__ status)
-{
-    constexpr int NH = NR / 2;
-    constexpr int EX = NR * LPC * 4;
-    constexpr long long EB = 2 * NR * LPC;
-    const int T = g.t1 - g.t0;
-    const bool on = lane < LPC;
-    const unsigned full = bar_full(bars_s, wb, 0), empty = bar_empty(bars_s, wb, 0);
-    block_sync(n_sync);
-#pragma unroll
-    for (int e = 0; e < kXR; e++) mbar_arrive(empty + 8u * e); // every entry starts out free
-    bool broken = false;
-#pragma unroll 1
-    for (int s = 0; s < T; s++) {
-        uint32_t a[NR], w[NH];
-        if (!mbar_wait(full + 8u * (s % kXR), (unsigned)((s / kXR) & 1), broken) && lane == 0) atomicOr(status, kStatusSpinTimeout);
-        xch_read<NR, LPC>(x_last + (s % kXR) * EX, li.sl, a);
-        warp_arrive(empty + 8u * (s % kXR), lane);
+    if (exp && dst) { // the state after the last step
+        xch_read<NR, LPC>(x_last + ((T & 1) ? x_stride : 0), li.sl, a);
+        uint32_t w[NH];
         state_to_words<NR>(a, dst_tag, w);
-        if (on) {
-            uint8_t *e = dst + (long long)s * EB + (long long)li.sl * 4;
+        uint8_t *e = dst + (long long)(T - 1) * EB + lane_off;
 #pragma unroll
-            for (int k = 0; k < NH; k++) st_relaxed(e + (long long)k * LPC * 4, w[k]);
-        }
+        for (int k = 0; k < NH; k++) st_relaxed(e + (long long)k * LPC * 4, w[k]);
     }
 }
 
 template <int NR, int LPC, bool FULL, bool IL>
-__global__ void __launch_bounds__((sweep_warps_max(NR) + 2) * 32)
+__global__ void __launch_bounds__((sweep_warps_max(NR) + 1) * 32)
     k_sgm_sweeps(const uint8_t *__restrict__ fused, Dims d, SweepPlan pl, uint8_t *__restrict__ vols, uint8_t *__restrict__ mailbox, int *__restrict__ status, unsigned one)
 {
     constexpr int CPW = 32 / LPC;
     constexpr int EX = NR * LPC * 4;
-    constexpr long long EB = 2 * NR * LPC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // ---- which sweep, which block of it: blocks are dealt round-robin over the sweeps that still have blocks at that
@@ -517,58 +479,42 @@ __global__ void __launch_bounds__((sweep_warps_max(NR) + 2) * 32)
     const int s_id = pl.lvl_sweep[lvl][rel % pl.lvl_n[lvl]];
     const int b = pl.lvl_pos[lvl] + rel / pl.lvl_n[lvl];
     const SweepGeo &g = pl.g[s_id];
-    const int nw = pl.nw, CH = nw * CPW;
-    const int T = g.t1 - g.t0;
+    const int nw = g.nw, CH = nw * CPW;
     const int slots_left = g.n1 - g.n0 + g.lead - b * CH; // slots from this block's first to the sweep's last chain
     const int last_e = slots_left < CH ? slots_left : CH;
     const int n_live = (last_e + CPW - 1) / CPW;
+    const int n_sync = (n_live + 1) * 32;
     LaneInfo<NR, LPC, FULL> li;
     li.init(lane, d.D);
     opaque(li.up_mask); opaque(li.dn_mask);
     li.one = one; // a kernel argument: the only 1 neither nvvm nor ptxas can fold (add_fma)
-    // shared memory: the barriers of nw + 1 warp boundaries, the exchange rings of CH + 1 chain boundaries, the warps' cost rings
-    const unsigned bars_s = (unsigned)__cvta_generic_to_shared(smem_raw);
-    const unsigned x_s = bars_s + (unsigned)((sweep_warps_max(NR) + 1) * 2 * kXR * 8);
-    const unsigned rings_s = x_s + (unsigned)(CH + 1) * (kXR * EX);
-    // who feeds boundary 0, who drains the last boundary
-    const bool first_line_block = g.row && g.n0 == 0 && b == 0; // its first warp holds the first line and reads nothing
-    const bool has_import = !first_line_block && T > 1;
-    uint8_t *dst = nullptr;
-    unsigned dst_tag = 0u;
-    if (b < g.nblk - 1) { dst = mailbox + (g.mb_off + (long long)b * T) * EB; dst_tag = pl.tagword; }
-    else if (g.row && g.band_out) dst = g.band_out;
-    const int n_sync = (n_live + (has_import ? 1 : 0) + (dst ? 1 : 0)) * 32;
-    for (int k = threadIdx.x; k < (n_live + 1) * 2 * kXR; k += blockDim.x) mbar_init(bars_s + 8u * k, 32); // the 32 lanes of one arriving warp each
-    if (warp == nw) {
-        if (has_import) import_warp<NR, LPC, FULL>(li, g, b, CH, mailbox, pl.tagword, x_s, bars_s, lane, n_sync, status);
+    const unsigned x_s = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const int x_stride = (CH + 1) * EX;
+    if (warp == pl.nw_max) {
+        mailbox_warp<NR, LPC, FULL>(li, g, b, CH, last_e, mailbox, pl.tagword, x_s, x_stride, lane, n_sync, status);
         return;
     }
-    if (warp == nw + 1) {
-        if (dst) export_warp<NR, LPC, FULL>(li, g, dst, dst_tag, x_s + (unsigned)last_e * (kXR * EX), bars_s, n_live, lane, n_sync, status);
-        return;
-    }
-    if (warp >= n_live) return;
-    // The scheduler prefers the warp with the highest id. A pipeline drains when its consumers are served first, so the
-    // chains are dealt to the warps in reverse: warp n_live - 1 is the first stage (position 0) and warp 0 the last.
-    const int pos = n_live - 1 - warp;
+    if (warp >= n_live) return; // (also the warps between this sweep's nw and nw_max)
     const int sub = lane / LPC;
-    const int cl = pos * CPW + sub;         // slot within the block
+    const int cl = warp * CPW + sub;        // slot within the block
     const int u = b * CH + cl;              // slot within the sweep
     int n = g.n0 + u - g.lead;
     const bool alive = u >= g.lead && n < g.n1;
     n = n < g.n0 ? g.n0 : n >= g.n1 ? g.n1 - 1 : n; // dead slots shadow a real chain (their stores are off)
     const bool car = alive && n >= g.car0 && n < g.car1;
-    const unsigned ring_s = rings_s + (unsigned)warp * (kRing * CPW * 2 * NR * LPC);
-    uint8_t *vol = vols + (size_t)g.vol * (size_t)d.cells;
-    // warp boundary w separates warp w - 1 (or the import warp) from warp w; boundary n_live separates the last warp from
-    // the export warp
-    const int in_wb = (pos > 0 || has_import) ? pos : -1;
-    const int out_wb = (pos + 1 < n_live || dst) ? pos + 1 : -1;
-    const bool first_line_warp = first_line_block && pos == 0; // holds chain 0 in its last sub-chain, the others are dead
+    const unsigned ring_s = x_s + 2u * (unsigned)x_stride + (unsigned)warp * (kRing * CPW * 2 * NR * LPC);
+    uint8_t *vol = vols + (size_t)g.vol * (size_t)pl.vol_stride;
+    const bool first_line_warp = g.row && g.n0 == 0 && b == 0 && warp == 0; // holds chain 0 in its last sub-chain, the others are dead
     const bool any_car = __any_sync(kFull, car);
-    if (first_line_warp) sweep_warp<NR, LPC, FULL, IL, 2>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, bars_s, in_wb, out_wb, lane, n_sync, status);
-    else if (!any_car) sweep_warp<NR, LPC, FULL, IL, 1>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, bars_s, in_wb, out_wb, lane, n_sync, status);
-    else sweep_warp<NR, LPC, FULL, IL, 0>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, bars_s, in_wb, out_wb, lane, n_sync, status);
+#ifdef SISTER_DEBUG_HOOKS
+    if (threadIdx.x == 0 && blockIdx.x < 2048) { g_sweep_times[blockIdx.x][0] = global_ns(); g_sweep_times[blockIdx.x][2] = sm_id(); g_sweep_times[blockIdx.x][3] = (unsigned long long)s_id * 65536ull + (unsigned)b; }
+#endif
+    if (first_line_warp) sweep_warp<NR, LPC, FULL, IL, 2>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, x_stride, lane, n_sync);
+    else if (!any_car) sweep_warp<NR, LPC, FULL, IL, 1>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, x_stride, lane, n_sync);
+    else sweep_warp<NR, LPC, FULL, IL, 0>(fused, vol, li, g, d.D, n, alive, car, cl, ring_s, x_s, x_stride, lane, n_sync);
+#ifdef SISTER_DEBUG_HOOKS
+    if (threadIdx.x == 0 && blockIdx.x < 2048) g_sweep_times[blockIdx.x][1] = global_ns();
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------- final sum + WTA + encode
@@ -580,14 +526,13 @@ __device__ __forceinline__ uint2 ldg8(const uint8_t *p) { return __ldg(reinterpr
 // Eight lanes per pixel, each lane owns 8-byte chunks sub, sub + 8, ... of the pixel's D bytes in all five volumes.
 // grid-stride over groups of 4 pixels per warp.
 template <bool IL>
-__global__ void __launch_bounds__(256, 6) k_sgm_final(const uint8_t *__restrict__ fused, const uint8_t *__restrict__ vols, Dims d, Roi roi,
+__global__ void __launch_bounds__(256, 6) k_sgm_final(const uint8_t *__restrict__ fused, const uint8_t *__restrict__ vols, size_t vol_stride, Dims d, Roi roi,
                                                    uint16_t *__restrict__ sum, int16_t *__restrict__ raw_disp, uint16_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const int D = d.D, nchunk = D >> 3;
-    const size_t cells = (size_t)d.cells;
     const int wroi = roi.c1 - roi.c0;
     const long long npx = (long long)(roi.r1 - roi.r0) * wroi; // pixels of the region of interest, row-major
     for (long long base = warp0 * 4; base < npx; base += nwarps * 4) {
@@ -613,7 +558,7 @@ __global__ void __launch_bounds__(256, 6) k_sgm_final(const uint8_t *__restrict_
                 const uint2 cc = ldg8(fused + off);
                 uint2 qq[4];
 #pragma unroll
-                for (int v = 0; v < 4; v++) qq[v] = ldg8(vols + (size_t)v * cells + off);
+                for (int v = 0; v < 4; v++) qq[v] = ldg8(vols + (size_t)v * vol_stride + off);
                 uint32_t S[4]; // 8 cells as packed u16: S[k] = bytes 2k, 2k + 1 of the chunk
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
@@ -709,7 +654,7 @@ static Roi make_roi(const Dims &d, bool full_frame)
 static inline long long entry_bytes(const Dims &d) { return 2LL * d.nr * d.lpc; }
 
 // The four sweeps of a frame restricted to the region `r` and the row band [b0, b1); sweeps not in `mask` get no blocks.
-static void plan_sweeps(const Dims &d, const Roi &r, int b0, int b1, unsigned mask, int nw, SweepPlan &pl)
+static void plan_sweeps(const Dims &d, const Roi &r, int b0, int b1, unsigned mask, const int (&nw)[4], SweepPlan &pl)
 {
     const int D8 = d.D >> 3, Wp = d.Wp, Hp = d.Hp, cpw = 32 / d.lpc;
     long long entries = 0;
@@ -741,12 +686,13 @@ static void plan_sweeps(const Dims &d, const Roi &r, int b0, int b1, unsigned ma
         }
         const bool empty = !((mask >> s) & 1u) || g.n1 <= g.n0 || g.t1 <= g.t0;
         g.lead = (g.row && g.n0 == 0) ? cpw - 1 : 0;
-        g.nblk = empty ? 0 : (g.n1 - g.n0 + g.lead + nw * cpw - 1) / (nw * cpw);
+        g.nw = nw[s];
+        g.nblk = empty ? 0 : (g.n1 - g.n0 + g.lead + nw[s] * cpw - 1) / (nw[s] * cpw);
         g.mb_off = entries;
         entries += (long long)g.nblk * (g.t1 - g.t0);
     }
     pl.entries = entries;
-    pl.nw = nw;
+    pl.nw_max = std::max(std::max(nw[0], nw[1]), std::max(nw[2], nw[3]));
     // deal the blocks round-robin: level L covers the positions at which the same set of sweeps still has blocks
     int order[4] = {0, 1, 2, 3};
     std::sort(order, order + 4, [&](int a, int b) { return pl.g[a].nblk < pl.g[b].nblk; });
@@ -767,9 +713,9 @@ static void plan_sweeps(const Dims &d, const Roi &r, int b0, int b1, unsigned ma
     pl.total_blocks = vid;
 }
 
-size_t sgm_mailbox_bytes(int max_w, int max_h, int max_d)
+size_t sgm_mailbox_bytes(int max_w, int max_h, int max_d, int band_rows)
 {
-    const long long Wp = max_w + 2LL * max_d, Hp = max_h + 2LL * max_d;
+    const long long Wp = max_w + 2LL * max_d, Hp = band_rows > 0 ? band_rows : max_h + 2LL * max_d; // a band runs its rows only
     long long eb = 0;
     for (int D = 8; D <= max_d; D += 8) {
         Dims d;
@@ -790,33 +736,55 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
 {
     constexpr int CPW = 32 / LPC;
     const void *kernel = (const void *)k_sgm_sweeps<NR, LPC, FULL, IL>;
-    auto smem_for = [&](int nw) { return (size_t)(sweep_warps_max(NR) + 1) * 2 * kXR * 8 + (size_t)kXR * (nw * CPW + 1) * NR * LPC * 4 + (size_t)nw * kRing * CPW * 2 * NR * LPC; };
+    auto smem_for = [&](int nw) { return (size_t)2 * (nw * CPW + 1) * NR * LPC * 4 + (size_t)nw * kRing * CPW * 2 * NR * LPC; };
     constexpr int kWarpsMax = sweep_warps_max(NR);
     if (smem_for(kWarpsMax) > 48 * 1024) lc.fail(optin_dynamic_smem(kernel, smem_for(kWarpsMax)));
-    // Compute warps per block. The blocks of a sweep are a pipeline: it runs at the pace of its slowest block, and a block's
-    // pace is set by how many warps share its SM's issue slots. So the choice is the one that spreads the warps most evenly
-    // over the SMs -- the fewest compute warps on the busiest SM, blocks being dealt round-robin -- among those for which the
-    // whole pipeline is resident at once (a block that has to wait for a slot starts its sweep late, which costs up to a
-    // whole sweep of time, not just its own share); ties go to the larger block (fewer hand-overs through global memory).
+    // Compute warps per block, per sweep. The blocks of a sweep are a pipeline that runs at the pace of its slowest block, and
+    // a block's pace is its number of warps (they share one SM's issue slots); a sweep of T steps with c warps per block
+    // therefore takes about T * c. The choice: the smallest time budget B such that c_s = B / T_s warps per block (within
+    // the limits) need no more blocks than are resident at once -- long sweeps get small blocks, short sweeps large ones,
+    // and all of them finish together. (A block that has to wait for a slot starts its sweep late, which costs up to a whole
+    // sweep of time, not just its own share.)
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     SweepPlan pl;
-    int nw = kSweepWarpsMin;
-    long long best = -1;
-    for (int cand = kWarpsMax; cand >= kSweepWarpsMin; cand--) {
-        plan_sweeps(d, roi, b0, b1, mask, cand, pl);
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (cand + 2) * 32, smem_for(cand)) != cudaSuccess) per_sm = 0;
-        const long long on_busiest = (pl.total_blocks + n_sm - 1) / n_sm;
-        // not resident at once: the sweeps run in waves, every wave a whole sweep long
-        const long long cost = on_busiest <= per_sm ? on_busiest * cand : (1LL << 40) + on_busiest * cand;
-        if (best < 0 || cost < best) { best = cost; nw = cand; }
+    int nw[4] = {kWarpsMax, kWarpsMax, kWarpsMax, kWarpsMax};
+    plan_sweeps(d, roi, b0, b1, mask, nw, pl); // chains and steps of every sweep (they do not depend on the block size)
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (kWarpsMax + 1) * 32, smem_for(kWarpsMax)) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long capacity = (long long)per_sm * n_sm;
+    long long best_cost = -1;
+    for (int s0 = 0; s0 < 4; s0++) {
+        if (pl.g[s0].nblk == 0) continue;
+        for (int c0 = kSweepWarpsMin; c0 <= kWarpsMax; c0++) {
+            const long long budget = (long long)(pl.g[s0].t1 - pl.g[s0].t0) * c0;
+            int cand[4];
+            long long blocks = 0, cost = 0;
+            for (int k = 0; k < 4; k++) {
+                const SweepGeo &g = pl.g[k];
+                cand[k] = kWarpsMax;
+                if (g.nblk == 0) continue;
+                const long long T = g.t1 - g.t0;
+                cand[k] = (int)std::min<long long>(kWarpsMax, std::max<long long>(kSweepWarpsMin, budget / T));
+                blocks += (g.n1 - g.n0 + g.lead + cand[k] * CPW - 1) / (cand[k] * CPW);
+                cost = std::max(cost, T * cand[k]);
+            }
+            if (blocks > capacity) continue;
+            cost *= (blocks + n_sm - 1) / n_sm; // blocks that share an SM share its issue slots
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; for (int k = 0; k < 4; k++) nw[k] = cand[k]; }
+        }
     }
 #ifdef SISTER_DEBUG_HOOKS
-    if (const char *e = getenv("SISTER_DEBUG_SWEEP_NW")) nw = std::min(std::max(atoi(e), kSweepWarpsMin), kWarpsMax); // measurement aid
+    if (const char *e = getenv("SISTER_DEBUG_SWEEP_NW")) { // measurement aid: "row,col" compute warps per block
+        int a = 0, b = 0;
+        if (sscanf(e, "%d,%d", &a, &b) == 2) { nw[0] = nw[2] = std::min(std::max(a, kSweepWarpsMin), kWarpsMax); nw[1] = nw[3] = std::min(std::max(b, kSweepWarpsMin), kWarpsMax); }
+    }
 #endif
     plan_sweeps(d, roi, b0, b1, mask, nw, pl);
+#ifdef SISTER_DEBUG_HOOKS
+    if (getenv("SISTER_DEBUG_SWEEP_STRIDE0")) for (int k = 0; k < 4; k++) pl.g[k].st8 = 0; // measurement aid: every step on the chain's first cell (no DRAM)
+#endif
     if (pl.total_blocks == 0) return;
     const long long eb = entry_bytes(d);
     if ((size_t)(pl.entries * eb) > sc.mailbox_bytes) { lc.fail(cudaErrorMemoryAllocation); return; }
@@ -832,7 +800,7 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
     // launch of the same geometry; anything else clears the mailbox first
     const unsigned long long key = ((unsigned long long)d.W << 48) ^ ((unsigned long long)d.H << 32) ^ ((unsigned long long)d.D << 20) ^
                                    ((unsigned long long)roi.r0 << 10) ^ ((unsigned long long)(unsigned)b0 * 0x9E3779B97F4A7C15ull) ^
-                                   ((unsigned long long)(unsigned)b1 * 0xC2B2AE3D27D4EB4Full) ^ ((unsigned long long)mask << 4) ^ (unsigned long long)nw;
+                                   ((unsigned long long)(unsigned)b1 * 0xC2B2AE3D27D4EB4Full) ^ ((unsigned long long)mask << 4) ^ (unsigned long long)(nw[0] * 32 + nw[1]);
     if (key != sc.geo_key || sc.epoch == 0) {
         lc.fail(cudaMemsetAsync(sc.mailbox, 0, (size_t)(pl.entries * eb), st));
         sc.geo_key = key;
@@ -841,7 +809,8 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
     sc.epoch = sc.epoch % 15 + 1;
     const unsigned e = sc.epoch;
     pl.tagword = ((e & 1u) << 7) | (((e >> 1) & 1u) << 15) | (((e >> 2) & 1u) << 23) | (((e >> 3) & 1u) << 31);
-    k_sgm_sweeps<NR, LPC, FULL, IL><<<(unsigned)pl.total_blocks, (nw + 2) * 32, smem_for(nw), st>>>(fused, d, pl, sc.vols, sc.mailbox, status, 1u);
+    pl.vol_stride = sc.vol_stride ? (long long)sc.vol_stride : d.cells;
+    k_sgm_sweeps<NR, LPC, FULL, IL><<<(unsigned)pl.total_blocks, (pl.nw_max + 1) * 32, smem_for(pl.nw_max), st>>>(fused, d, pl, sc.vols - sc.row_shift, sc.mailbox, status, 1u);
     lc.add();
 }
 
@@ -871,19 +840,22 @@ static void launch_sweeps_lpc(const uint8_t *fused, const Dims &d, const Roi &ro
 static void launch_sweeps(const uint8_t *fused, const Dims &d, const Roi &roi, int b0, int b1, unsigned mask, const uint8_t *band_in, uint8_t *band_out,
                           SgmScratch &sc, int *status, cudaStream_t st, LaunchCounter &lc)
 {
+#ifdef SISTER_DEBUG_HOOKS
+    if (const char *e = getenv("SISTER_DEBUG_SWEEP_MASK")) mask &= (unsigned)atoi(e); // measurement aid: run some of the sweeps only
+#endif
     if (d.lpc == 8) launch_sweeps_lpc<8, 12>(fused, d, roi, b0, b1, mask, band_in, band_out, sc, status, st, lc); // four chains per warp
     else launch_sweeps_lpc<16, 16>(fused, d, roi, b0, b1, mask, band_in, band_out, sc, status, st, lc);           // two (D <= 512, check_shape)
 }
 
-static void launch_final(const uint8_t *fused, const uint8_t *vols, const Dims &d, const Roi &roi, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
-                         cudaStream_t st)
+static void launch_final(const uint8_t *fused, const uint8_t *vols, size_t vol_stride, const Dims &d, const Roi &roi, uint16_t *sum, int16_t *raw_disp,
+                         uint16_t *out, cudaStream_t st)
 {
     const long long groups = ((long long)(roi.r1 - roi.r0) * (roi.c1 - roi.c0) + 3) / 4;
     if (groups <= 0) return;
     long long blocks = (groups + 7) / 8;
     if (blocks > 148LL * 64) blocks = 148LL * 64;
-    if (d.interleaved) k_sgm_final<true><<<(unsigned)blocks, 256, 0, st>>>(fused, vols, d, roi, sum, raw_disp, out);
-    else k_sgm_final<false><<<(unsigned)blocks, 256, 0, st>>>(fused, vols, d, roi, sum, raw_disp, out);
+    if (d.interleaved) k_sgm_final<true><<<(unsigned)blocks, 256, 0, st>>>(fused, vols, vol_stride, d, roi, sum, raw_disp, out);
+    else k_sgm_final<false><<<(unsigned)blocks, 256, 0, st>>>(fused, vols, vol_stride, d, roi, sum, raw_disp, out);
 }
 
 void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, SgmScratch &sc, uint16_t *sum, int16_t *raw_disp, uint16_t *out,
@@ -891,7 +863,7 @@ void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, SgmScratch
 {
     const Roi roi = make_roi(d, full_frame);
     launch_sweeps(fused, d, roi, 0, d.Hp, 0xFu, nullptr, nullptr, sc, status, st, lc);
-    launch_final(fused, sc.vols, d, roi, sum, raw_disp, out, st);
+    launch_final(fused, sc.vols - sc.row_shift, sc.vol_stride ? sc.vol_stride : (size_t)d.cells, d, roi, sum, raw_disp, out, st);
     lc.add();
 }
 
@@ -905,7 +877,7 @@ void launch_sgm_band(int what, const uint8_t *fused, const Dims &d, int band_r0,
     if (what == 3) {
         roi.r0 = roi.r0 > band_r0 ? roi.r0 : band_r0;
         roi.r1 = roi.r1 < band_r1 ? roi.r1 : band_r1;
-        launch_final(fused, sc.vols, d, roi, nullptr, raw_disp, out, st);
+        launch_final(fused, sc.vols - sc.row_shift, sc.vol_stride ? sc.vol_stride : (size_t)d.cells, d, roi, nullptr, raw_disp, out, st);
         lc.add();
     } else {
         launch_sweeps(fused, d, roi, band_r0, band_r1, what == 1 ? 0x3u : 0xCu, state_in, state_out, sc, status, st, lc);

@@ -30,6 +30,31 @@ def test_bands_on_one_gpu_equal_the_single_band_map(w, h, D, world, mode):
     assert (got == want).all(), f"{(got != want).sum()} pixels differ"
 
 
+@pytest.mark.parametrize("w,h,D,world", [(96, 64, 32, 3), (128, 96, 64, 4), (52, 88, 136, 2)])
+def test_band_contexts_hold_a_band_of_the_volumes_only(w, h, D, world):
+    """sister_create_band: the fused and pair volumes of a slot hold max_band_rows rows of the padded frame; G such slots
+    together hold one frame's worth, and the banded map is still the single-GPU map. Full-frame calls are refused."""
+    import sister_b200
+    from sister_b200.bands import EngineBandWorker, as_uint16, band_rows, run_bands_in_process
+
+    views = make_rig(w, h, D, seed=77 + world, channels=1)
+    hp = h + 2 * D
+    rows_max = max(b - a for a, b in (band_rows(hp, world, r) for r in range(world)))
+    with sister_b200.Engine(w, h, D, n_slots=1) as eng:
+        want = eng.compute(views, D, mode_mask=1)[0]
+    with sister_b200.Engine(w, h, D, n_slots=world, max_band_rows=rows_max) as eng:
+        workers = [EngineBandWorker(eng, views, D, r, world, mode=0, slot=r) for r in range(world)]
+        rows = run_bands_in_process(workers)
+        got = np.concatenate([as_uint16(r) for r in rows], axis=0)
+        assert (got == want).all(), f"{(got != want).sum()} pixels differ"
+        with pytest.raises(sister_b200.SisterError) as e:
+            eng.compute(views, D, mode_mask=1)
+        assert e.value.code == -3
+    with pytest.raises(sister_b200.SisterError):
+        with sister_b200.Engine(w, h, D, n_slots=1, max_band_rows=rows_max - 1) as eng:
+            EngineBandWorker(eng, views, D, 0, world, mode=0, slot=0).submit()
+
+
 def test_bands_over_nccl_when_the_box_has_two_gpus():
     import torch
 
