@@ -1,11 +1,12 @@
 """Row-band sharding of ONE large frame over the GPUs of one box (BASELINE.json configs[3]).
 
-Each rank owns a contiguous band of rows of the PADDED frame. The volumes (fused cost, eight path volumes, final sum)
-exist for the band only; staging, census, raw-cost WTA and masks are recomputed for the whole frame by every rank
-(include/sister_b200.h, "Row bands"). The row paths of SGM are band-local. The column and diagonal paths cross the
-bands: pass 0 flows from rank 0 down to rank G-1, pass 1 from rank G-1 up to rank 0, and each rank continues a path
-from the state its neighbour left (3 * Wp * D bytes per pass, exact -- no approximate overlapping halos). While rank t
-works on pass 0, rank G-1-t works on pass 1, so the two wavefronts overlap; everything else is fully parallel.
+Each rank owns a contiguous band of rows of the PADDED frame. The volumes (fused cost, four SGM pair volumes, final sum)
+are filled for the band only -- and, in an Engine made with max_band_rows, allocated for it only; staging, census, raw-cost
+WTA and masks are recomputed for the whole frame by every rank (include/sister_b200.h, "Row bands"). Every sweep of the
+aggregation carries a diagonal path, so all of it crosses the bands: pass 0 flows from rank 0 down to rank G-1, pass 1
+from rank G-1 up to rank 0, and each rank continues from the state its neighbour left (band_state_bytes per pass, exact --
+no approximate overlapping halos). While rank t works on pass 0, rank G-1-t works on pass 1, so the two wavefronts
+overlap; everything else is fully parallel.
 
 `band_program` is the per-rank list of operations; the order of the two messages a pair of neighbours exchanges is the
 same on both sides (by the time slot the message is produced in), so blocking sends and receives cannot deadlock,
@@ -88,8 +89,8 @@ def simulate_programs(world: int) -> int:
 
 def compute_banded(worker, world: int, rank: int, group=None):
     """Run this rank's band. `worker` provides
-         submit()                              -- whole-frame stages, fused cost and row paths of the band
-         vertical(pass, state_in, want_out)    -- column / diagonal paths of one pass; state_in / return value are torch
+         submit()                              -- whole-frame stages and the fused cost of the band
+         vertical(pass, state_in, want_out)    -- the four paths of one pass inside the band; state_in / return value are torch
                                                   uint8 tensors on the worker's device (or None)
          new_state()                           -- an empty state tensor to receive into
          finish()                              -- final WTA; returns this band's rows of the H x W map (torch int16 tensor
@@ -116,8 +117,8 @@ def compute_banded(worker, world: int, rank: int, group=None):
 
 def run_bands_in_process(workers):
     """All bands in ONE process (workers[r] is rank r's worker): the same programs, messages handed over directly.
-    This is how the tests run G bands on one GPU (one slot per band), and a way to bound the memory of a very large frame
-    on a single GPU. Returns the list of the bands' rows."""
+    This is how the tests run G bands on one GPU (one slot per band; with an Engine(max_band_rows=...) the G slots together
+    hold one frame's worth of volumes). Returns the list of the bands' rows."""
     world = len(workers)
     for w in workers:
         w.submit()
