@@ -157,7 +157,7 @@ int run_pipeline(sister_ctx *ctx, Slot &s, const uint8_t *const in_views[5], int
     launch_match_wta(s.d_census, d, view_mask, s.d_wtaL, s.d_wtaR, s.st, ctx->lc);
     end_stage(ctx, s);
     begin_stage(ctx, s, SISTER_STAGE_MASK);
-    launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, view_mask, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.st, ctx->lc);
+    launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, view_mask, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.d_status, s.st, ctx->lc);
     end_stage(ctx, s);
     // Several modes in one call (the reference class always runs all three, hpp:77-89): one fuse pass evaluates every Hamming
     // distance once and writes the horizontal, the vertical and the multiview (their sum, hpp:262-276) volume together.
@@ -482,7 +482,7 @@ int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev
     launch_prep(views_dev[0], (size_t)stride, w * channels, channels, d, s.d_oriented, s.st, ctx->lc);
     launch_census(s.d_oriented, d, s.d_census, s.st, ctx->lc);
     launch_match_wta(s.d_census, d, vm, s.d_wtaL, s.d_wtaR, s.st, ctx->lc);
-    launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, vm, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.st, ctx->lc);
+    launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, vm, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.d_status, s.st, ctx->lc);
     // a band context's volumes start with the band's first row: every kernel addresses rows of the padded frame, so the
     // bases are moved back by the rows that are not there (only the band's rows are ever touched)
     s.sgm.row_shift = ctx->band_rows > 0 ? (size_t)band_row0 * (size_t)d.Wp * (size_t)d.D : 0;
@@ -770,7 +770,7 @@ int sister_stereo(sister_ctx *ctx, const uint8_t *center, const uint8_t *side, i
     launch_wta_right_sum(s.d_sum, d, s.d_wtaR, s.st, ctx->lc);
     // median on both maps (hpp:139-140), LRC (hpp:143)
     ctx->lc.cur_stage = SISTER_STAGE_MASK;
-    launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, 0x1u, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.st, ctx->lc);
+    launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, 0x1u, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.d_status, s.st, ctx->lc);
     SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
     SCK(cudaGetLastError());
     SCK(cudaStreamSynchronize(s.st));

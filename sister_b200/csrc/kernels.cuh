@@ -49,7 +49,7 @@ void launch_match_wta(const unsigned long long *census, const Dims &d, unsigned 
                       cudaStream_t st, LaunchCounter &lc);
 // in-place-semantics 3x3 median (postprocess.cpp:15-71 with src == dst), LRC (postprocess.cpp:318-341), masks (hpp:201-251)
 void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims &d, unsigned view_mask, int16_t *medL,
-                            int16_t *medR, int16_t *lr_final, uint8_t *masks, cudaStream_t st, LaunchCounter &lc);
+                            int16_t *medR, int16_t *lr_final, uint8_t *masks, int *status, cudaStream_t st, LaunchCounter &lc);
 // fused volume C = sum_v mask_v * cost_v as uint8 (hpp:255-277); view_mask selects the mode's views
 // row_lo / row_hi: image rows to produce (whole tiles; the full frame is 0, Hp)
 // fused_h / fused_v (both or neither, with view_mask 0xF): the same pass also writes the fused volumes of the horizontal

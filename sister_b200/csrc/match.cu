@@ -357,6 +357,194 @@ __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wta
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
+// ---- the same recurrence with the warps running free behind each other (frames of 256 .. 2048 view columns, widths a
+// multiple of 4). In flat terms out[p] depends on out[p - w - 1 .. p - w + 1]: a column chunk of a row needs the same chunk
+// of the row above and one pixel of either neighbouring chunk -- not the whole row. So warp c owns the 128 columns
+// [128c, 128c + 128) (four pixels = two packed words per lane), walks down the rows, and waits only for its two neighbours
+// to have finished the row above (the first chunk's left neighbour is the last chunk two rows up, the last chunk's right
+// neighbour is the first chunk of the SAME row: the flat wrap-around of postprocess.cpp:31-67). No block barrier: a row
+// costs one neighbour hand-over (an mbarrier phase per warp and row, two barriers per warp alternating with the row parity
+// so that a waiter can never be two phases behind). The filtered row above stays in the lanes' registers; neighbouring
+// lanes exchange their edge pixels with shuffles, neighbouring warps through one boundary word per side and row in shared
+// memory (ring of 4 rows). Raw rows are streamed per warp with cp.async (kMed2Depth rows ahead) into the warp's own ring
+// of [32 x 2 words | left halo word | right halo word]. The row loop is bound by instruction issue (13 warps on one SM),
+// which is why a lane takes four pixels: the hand-over and the addressing are paid once per 128 columns.
+constexpr int kMed2Depth = 8, kMed2MaxWarps = 16, kMed2Slot = 264; // bytes of one raw row of a warp
+
+__device__ __forceinline__ void med_mbar_init(unsigned a, int c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(c) : "memory"); }
+__device__ __forceinline__ void med_mbar_arrive(unsigned a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory"); }
+// bounded by time: a broken pipeline must never hang the device (returns false after 4 s)
+template <int WAIT>
+__device__ __forceinline__ bool med_mbar_wait(unsigned a, unsigned parity)
+{
+    unsigned ok;
+    unsigned long long t0 = 0;
+    for (unsigned n = 0;; n++) {
+        if (WAIT == 1)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 100000;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        else if (WAIT == 3)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return true;
+        if (WAIT >= 2) __nanosleep(32);
+        if ((n & 255u) != 255u) continue;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 4000000000ull) return false;
+    }
+}
+
+// grid 8 (one block per map), block 32 * ceil(max(wv) / 128)
+__device__ __forceinline__ uint32_t med_lds32(unsigned a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint2 med_lds64(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void med_sts32(unsigned a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
+
+// grid 8 (one block per map), block 32 * ceil(max(wv) / 128). Everything a row needs besides the median itself is kept to a
+// handful of instructions -- a warp's row is one serial instruction sequence and the rows are serial: shared memory is
+// addressed in its own window with offsets carried from row to row, the boundary loads and stores are one instruction for
+// the whole warp with per-lane addresses (no divergent branch), and the two special rows are a uniform branch.
+template <int WAIT>
+__global__ void __launch_bounds__(32 * kMed2MaxWarps) k_median_chunks(const int16_t *__restrict__ wtaL, const int16_t *__restrict__ wtaR,
+                                                                      Dims d, unsigned view_mask, int16_t *__restrict__ medL,
+                                                                      int16_t *__restrict__ medR, int *__restrict__ status)
+{
+    __shared__ __align__(8) unsigned long long bars[2 * kMed2MaxWarps];          // [warp][row parity]
+    __shared__ __align__(8) uint32_t bnd[4][kMed2MaxWarps][2];                   // [row & 3][warp][first word, last word]
+    __shared__ __align__(16) unsigned char rings[kMed2MaxWarps * kMed2Depth * kMed2Slot];
+    const int m = blockIdx.x, v = m >> 1;
+    if (!((view_mask >> v) & 1u)) return;
+    const int hv = view_rows(d, v), wv = view_cols(d, v);
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5, nch = (wv + 127) >> 7, L = nch - 1; // (the block is sized for the wider orientation)
+    const unsigned bars_s = (unsigned)__cvta_generic_to_shared(bars);
+    if (threadIdx.x < 2 * nch) med_mbar_init(bars_s + 8u * threadIdx.x, 32);
+    __syncthreads();
+    if (c >= nch) return;
+    const int N = hv * wv, p_lo = wv + 1, p_hi = N - wv - 5;
+    const int x = 128 * c + 4 * lane;                            // the lane's four columns x .. x + 3
+    const int nl = min(32, (wv - 128 * c) >> 2), last = nl - 1;  // lanes of this chunk that hold pixels (>= 2)
+    const bool on = lane < nl, first_lane = lane == 0, last_lane = lane == last;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(rings) + (unsigned)(c * (kMed2Depth * kMed2Slot));
+    const unsigned bnd_s = (unsigned)__cvta_generic_to_shared(bnd);
+    constexpr unsigned kRingBytes = kMed2Depth * kMed2Slot;
+    // ---- staging of the raw rows. Row j -> slot j % depth: 32 x (two words), then the word before the chunk and the word
+    // after it (flat neighbours, whatever row they belong to; nothing outside [0, N) is touched: the word before row 0 of
+    // chunk 0 and the word after the last row of the last chunk do not exist)
+    const char *gsrc = reinterpret_cast<const char *>(((m & 1) ? wtaR : wtaL) + (size_t)v * d.px + x);
+    const int halo_src = first_lane ? -4 : 8;
+    const unsigned own_dst = 8u * lane, halo_dst = first_lane ? 256u : 260u;
+    const int halo_j0 = first_lane ? (c == 0 ? 1 : 0) : (last_lane ? 0 : hv);           // rows [halo_j0, halo_j1] have the halo word
+    const int halo_j1 = (last_lane && !first_lane && c == L) ? hv - 2 : hv - 1;
+    const size_t row_bytes = (size_t)wv * 2;
+    unsigned st_off = 0; // slot of the next row to stage
+    int st_j = 0;
+    auto stage = [&]() {
+        if (st_j < hv) {
+            if (on) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(ring_s + st_off + own_dst), "l"(gsrc) : "memory");
+            if (st_j >= halo_j0 && st_j <= halo_j1)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(ring_s + st_off + halo_dst), "l"(gsrc + halo_src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        gsrc += row_bytes;
+        st_j++;
+        st_off += kMed2Slot;
+        if (st_off == kRingBytes) st_off = 0;
+    };
+    // the five window words of the raw row in slot offset rd for this lane: (x-1 x) (x x+1) (x+1 x+2) (x+2 x+3) (x+3 x+4)
+    unsigned rd_off = 0;
+    auto raw_row = [&](uint32_t (&w)[5]) {
+        const uint2 own = med_lds64(ring_s + rd_off + own_dst);
+        const uint32_t halo = med_lds32(ring_s + rd_off + halo_dst);
+        uint32_t left = __shfl_up_sync(0xFFFFFFFFu, own.y, 1), right = __shfl_down_sync(0xFFFFFFFFu, own.x, 1);
+        if (first_lane) left = halo;
+        if (last_lane) right = halo;
+        w[0] = __byte_perm(left, own.x, 0x5432); w[1] = own.x; w[2] = __byte_perm(own.x, own.y, 0x5432); w[3] = own.y;
+        w[4] = __byte_perm(own.y, right, 0x5432);
+        rd_off += kMed2Slot;
+        if (rd_off == kRingBytes) rd_off = 0;
+    };
+    // ---- hand-over with the neighbouring warps. Left: warp c - 1 at row r - 1 (chunk 0: the last chunk at row r - 2);
+    // right: warp c + 1 at row r - 1 (the last chunk: chunk 0 at row r). Lane 0 takes the left boundary word, every other
+    // lane the right one (only the chunk's last lane uses it).
+    const int lw = c > 0 ? c - 1 : L, ld = c > 0 ? 1 : 2, rw = c < L ? c + 1 : 0, rdl = c < L ? 1 : 0;
+    const int b_delta = first_lane ? ld : rdl;
+    const unsigned b_base = bnd_s + (first_lane ? 8u * lw + 4u : 8u * rw);
+    const unsigned my_bnd = bnd_s + 8u * c + (first_lane ? 0u : 4u);
+    const bool bnd_writer = first_lane || last_lane;
+    int16_t *gout = ((m & 1) ? medR : medL) + (size_t)v * d.px + x;
+
+    for (int j = 0; j < kMed2Depth - 1; j++) stage();
+    bool broken = false;
+    uint32_t q[5], s[5] = {0u, 0u, 0u, 0u, 0u};
+    uint32_t f0, f1; // this lane's part of the finished row above
+    // row 0 is copied unchanged
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kMed2Depth - 2) : "memory");
+    raw_row(q);
+    f0 = q[1]; f1 = q[3];
+    if (on) *reinterpret_cast<uint2 *>(gout) = make_uint2(f0, f1);
+    if (bnd_writer) med_sts32(my_bnd, first_lane ? f0 : f1);
+    med_mbar_arrive(bars_s + 8u * (2 * c));
+    stage();
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kMed2Depth - 2) : "memory");
+    raw_row(q);
+    for (int r = 1; r < hv; r++) {
+        stage();
+        gout += wv;
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(kMed2Depth - 2) : "memory"); // rows <= r + 1 have landed
+        if (r + 1 < hv) raw_row(s);
+        uint32_t fl = __shfl_up_sync(0xFFFFFFFFu, f1, 1), fr = __shfl_down_sync(0xFFFFFFFFu, f0, 1);
+        uint32_t v0 = q[1], v1 = q[3];
+        if (r < hv - 1) {
+            // the row above: this chunk is in the registers; one pixel of either neighbouring chunk
+            if (!broken) {
+                bool ok = true;
+                const int rl = r - ld, rr = r - rdl;
+                if (rl >= 0) ok = med_mbar_wait<WAIT>(bars_s + 8u * (2 * lw + (rl & 1)), (unsigned)((rl >> 1) & 1));
+                if (ok) ok = med_mbar_wait<WAIT>(bars_s + 8u * (2 * rw + (rr & 1)), (unsigned)((rr >> 1) & 1));
+                if (!ok) {
+                    broken = true;
+                    if (lane == 0) atomicOr(status, kStatusSpinTimeout);
+                }
+            }
+            const uint32_t edge = med_lds32(b_base + 128u * ((unsigned)(r - b_delta) & 3u)); // (row 1, chunk 0, lane 0: unused, out[w] = 0)
+            if (first_lane) fl = edge;
+            if (last_lane) fr = edge;
+            uint32_t l[5], md[5], h[5];
+            sort3p(__byte_perm(fl, f0, 0x5432), q[0], s[0], l[0], md[0], h[0]);
+            sort3p(f0, q[1], s[1], l[1], md[1], h[1]);
+            sort3p(__byte_perm(f0, f1, 0x5432), q[2], s[2], l[2], md[2], h[2]);
+            sort3p(f1, q[3], s[3], l[3], md[3], h[3]);
+            sort3p(__byte_perm(f1, fr, 0x5432), q[4], s[4], l[4], md[4], h[4]);
+            v0 = med3p(__vimax3_s16x2(l[0], l[1], l[2]), med3p(md[0], md[1], md[2]), __vimin3_s16x2(h[0], h[1], h[2]));
+            v1 = med3p(__vimax3_s16x2(l[2], l[3], l[4]), med3p(md[2], md[3], md[4]), __vimin3_s16x2(h[2], h[3], h[4]));
+            if (r == 1 || r == hv - 2) { // the first and the last filtered positions: postprocess.cpp:29,61-63
+                const int base = r * wv + x;
+                auto fix = [&](uint32_t val, uint32_t rawv, int p) -> uint32_t {
+                    if (p == wv) val &= 0xFFFF0000u;                                   // out[w] = 0
+                    else if (p < p_lo || p > p_hi) val = (val & 0xFFFF0000u) | (rawv & 0xFFFFu);
+                    if (p + 1 < p_lo || p + 1 > p_hi) val = (val & 0xFFFFu) | (rawv & 0xFFFF0000u);
+                    return val;
+                };
+                v0 = fix(v0, q[1], base);
+                v1 = fix(v1, q[3], base + 2);
+            }
+        }
+        f0 = v0; f1 = v1;
+        if (bnd_writer) med_sts32(my_bnd + 128u * ((unsigned)r & 3u), first_lane ? f0 : f1);
+        // (the last row has no dependencies and nobody waits for it: arriving for it could put this warp two phases ahead
+        // of a neighbour that still waits for row hv - 3 on the same barrier)
+        if (r < hv - 1) med_mbar_arrive(bars_s + 8u * (2 * c + (r & 1)));
+        if (on) *reinterpret_cast<uint2 *>(gout) = make_uint2(f0, f1);
+#pragma unroll
+        for (int k = 0; k < 5; k++) q[k] = s[k];
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
 // grid (ceil(wv/256), max(hv), 4), block 256
 __global__ void __launch_bounds__(256) k_lrc_mask(const int16_t *__restrict__ medL, const int16_t *__restrict__ medR, Dims d,
                                                   unsigned view_mask, int16_t *__restrict__ lr_final, uint8_t *__restrict__ masks)
@@ -381,13 +569,29 @@ __global__ void __launch_bounds__(256) k_lrc_mask(const int16_t *__restrict__ me
 }
 
 void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims &d, unsigned view_mask, int16_t *medL,
-                            int16_t *medR, int16_t *lr_final, uint8_t *masks, cudaStream_t st, LaunchCounter &lc)
+                            int16_t *medR, int16_t *lr_final, uint8_t *masks, int *status, cudaStream_t st, LaunchCounter &lc)
 {
     int m = d.Wp > d.Hp ? d.Wp : d.Hp;
-    const size_t med_smem = (size_t)(kMedRing + 4) * m * sizeof(int16_t);
-    lc.fail(optin_dynamic_smem((const void *)k_median, med_smem));
-    k_median<<<8, 1024, med_smem, st>>>(wtaL, wtaR, d, view_mask, medL, medR);
-    lc.add();
+    const int lo = d.Wp < d.Hp ? d.Wp : d.Hp;
+    if (lo >= 256 && m <= 128 * kMed2MaxWarps && d.Wp % 8 == 0 && d.Hp % 8 == 0) {
+        // warps free-running behind each other, one per 128 columns; the block is sized for the wider of the two frame
+        // orientations and the warps a narrower map does not need leave at once
+#ifdef SISTER_DEBUG_HOOKS
+        const char *e = getenv("SISTER_DEBUG_MED_VAR");
+        const int var = e ? atoi(e) : 0;
+#define MEDV(V) case V: k_median_chunks<V><<<8, 32 * ((m + 127) / 128), 0, st>>>(wtaL, wtaR, d, view_mask, medL, medR, status); break;
+        switch (var) { MEDV(0) MEDV(1) MEDV(2) MEDV(3) }
+#undef MEDV
+#else
+        k_median_chunks<0><<<8, 32 * ((m + 127) / 128), 0, st>>>(wtaL, wtaR, d, view_mask, medL, medR, status);
+#endif
+        lc.add();
+    } else {
+        const size_t med_smem = (size_t)(kMedRing + 4) * m * sizeof(int16_t);
+        lc.fail(optin_dynamic_smem((const void *)k_median, med_smem));
+        k_median<<<8, 1024, med_smem, st>>>(wtaL, wtaR, d, view_mask, medL, medR);
+        lc.add();
+    }
     dim3 grid((m + 255) / 256, m, 4);
     k_lrc_mask<<<grid, 256, 0, st>>>(medL, medR, d, view_mask, lr_final, masks);
     lc.add();
