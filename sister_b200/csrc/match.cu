@@ -374,23 +374,14 @@ constexpr int kMed2Depth = 8, kMed2MaxWarps = 16, kMed2Slot = 264; // bytes of o
 __device__ __forceinline__ void med_mbar_init(unsigned a, int c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(c) : "memory"); }
 __device__ __forceinline__ void med_mbar_arrive(unsigned a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory"); }
 // bounded by time: a broken pipeline must never hang the device (returns false after 4 s)
-template <int WAIT>
 __device__ __forceinline__ bool med_mbar_wait(unsigned a, unsigned parity)
 {
     unsigned ok;
     unsigned long long t0 = 0;
     for (unsigned n = 0;; n++) {
-        if (WAIT == 1)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 100000;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        else if (WAIT == 3)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        else
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
         if (ok) return true;
-        if (WAIT >= 2) __nanosleep(32);
         if ((n & 255u) != 255u) continue;
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
@@ -399,7 +390,6 @@ __device__ __forceinline__ bool med_mbar_wait(unsigned a, unsigned parity)
     }
 }
 
-// grid 8 (one block per map), block 32 * ceil(max(wv) / 128)
 __device__ __forceinline__ uint32_t med_lds32(unsigned a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint2 med_lds64(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void med_sts32(unsigned a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
@@ -408,7 +398,6 @@ __device__ __forceinline__ void med_sts32(unsigned a, uint32_t v) { asm volatile
 // handful of instructions -- a warp's row is one serial instruction sequence and the rows are serial: shared memory is
 // addressed in its own window with offsets carried from row to row, the boundary loads and stores are one instruction for
 // the whole warp with per-lane addresses (no divergent branch), and the two special rows are a uniform branch.
-template <int WAIT>
 __global__ void __launch_bounds__(32 * kMed2MaxWarps) k_median_chunks(const int16_t *__restrict__ wtaL, const int16_t *__restrict__ wtaR,
                                                                       Dims d, unsigned view_mask, int16_t *__restrict__ medL,
                                                                       int16_t *__restrict__ medR, int *__restrict__ status)
@@ -437,6 +426,7 @@ __global__ void __launch_bounds__(32 * kMed2MaxWarps) k_median_chunks(const int1
     const char *gsrc = reinterpret_cast<const char *>(((m & 1) ? wtaR : wtaL) + (size_t)v * d.px + x);
     const int halo_src = first_lane ? -4 : 8;
     const unsigned own_dst = 8u * lane, halo_dst = first_lane ? 256u : 260u;
+    const unsigned halo_rd = (first_lane || last_lane) ? halo_dst : own_dst; // (the other lanes do not use what they read here)
     const int halo_j0 = first_lane ? (c == 0 ? 1 : 0) : (last_lane ? 0 : hv);           // rows [halo_j0, halo_j1] have the halo word
     const int halo_j1 = (last_lane && !first_lane && c == L) ? hv - 2 : hv - 1;
     const size_t row_bytes = (size_t)wv * 2;
@@ -458,7 +448,7 @@ __global__ void __launch_bounds__(32 * kMed2MaxWarps) k_median_chunks(const int1
     unsigned rd_off = 0;
     auto raw_row = [&](uint32_t (&w)[5]) {
         const uint2 own = med_lds64(ring_s + rd_off + own_dst);
-        const uint32_t halo = med_lds32(ring_s + rd_off + halo_dst);
+        const uint32_t halo = med_lds32(ring_s + rd_off + halo_rd);
         uint32_t left = __shfl_up_sync(0xFFFFFFFFu, own.y, 1), right = __shfl_down_sync(0xFFFFFFFFu, own.x, 1);
         if (first_lane) left = halo;
         if (last_lane) right = halo;
@@ -503,8 +493,8 @@ __global__ void __launch_bounds__(32 * kMed2MaxWarps) k_median_chunks(const int1
             if (!broken) {
                 bool ok = true;
                 const int rl = r - ld, rr = r - rdl;
-                if (rl >= 0) ok = med_mbar_wait<WAIT>(bars_s + 8u * (2 * lw + (rl & 1)), (unsigned)((rl >> 1) & 1));
-                if (ok) ok = med_mbar_wait<WAIT>(bars_s + 8u * (2 * rw + (rr & 1)), (unsigned)((rr >> 1) & 1));
+                if (rl >= 0) ok = med_mbar_wait(bars_s + 8u * (2 * lw + (rl & 1)), (unsigned)((rl >> 1) & 1));
+                if (ok) ok = med_mbar_wait(bars_s + 8u * (2 * rw + (rr & 1)), (unsigned)((rr >> 1) & 1));
                 if (!ok) {
                     broken = true;
                     if (lane == 0) atomicOr(status, kStatusSpinTimeout);
@@ -576,15 +566,7 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
     if (lo >= 256 && m <= 128 * kMed2MaxWarps && d.Wp % 8 == 0 && d.Hp % 8 == 0) {
         // warps free-running behind each other, one per 128 columns; the block is sized for the wider of the two frame
         // orientations and the warps a narrower map does not need leave at once
-#ifdef SISTER_DEBUG_HOOKS
-        const char *e = getenv("SISTER_DEBUG_MED_VAR");
-        const int var = e ? atoi(e) : 0;
-#define MEDV(V) case V: k_median_chunks<V><<<8, 32 * ((m + 127) / 128), 0, st>>>(wtaL, wtaR, d, view_mask, medL, medR, status); break;
-        switch (var) { MEDV(0) MEDV(1) MEDV(2) MEDV(3) }
-#undef MEDV
-#else
-        k_median_chunks<0><<<8, 32 * ((m + 127) / 128), 0, st>>>(wtaL, wtaR, d, view_mask, medL, medR, status);
-#endif
+        k_median_chunks<<<8, 32 * ((m + 127) / 128), 0, st>>>(wtaL, wtaR, d, view_mask, medL, medR, status);
         lc.add();
     } else {
         const size_t med_smem = (size_t)(kMedRing + 4) * m * sizeof(int16_t);

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, golden_rigs, golden_views, grey_of
+import sister_b200
 from sister_b200.synth import make_rig
 
 pytestmark = pytest.mark.gpu
@@ -76,6 +77,26 @@ def test_every_stage_against_oracle(engine, oracle_lib, w, h, D, kind, seed, col
         assert (wl[v] == L.ravel()).all(), f"WTA-left, view {v}"
         assert (wr[v] == R.ravel()).all(), f"WTA-right, view {v}"
         assert (lr[v] == t["lr"][v]).all(), f"median + LRC, view {v}"
+    assert (masks == t["masks"]).all()
+
+
+@pytest.mark.parametrize("w,h,D,seed", [(240, 240, 8, 31), (248, 240, 8, 32), (376, 248, 8, 33), (1000, 264, 16, 34), (252, 244, 8, 35)])
+def test_median_kernels_by_frame_shape(oracle_lib, w, h, D, seed):
+    """The recursive median (postprocess.cpp:31-67) has two kernels: warps chained by neighbour hand-over (128 columns each) for
+    padded frames of 256 .. 2048 with sides a multiple of 8, one block barrier per row otherwise. Shapes: exactly two chunks,
+    a last chunk of two lanes (264 = 2 * 128 + 8), different chunk counts for the two orientations, nine chunks, and one
+    shape (268 x 260: multiples of 4, not of 8) that takes the barrier kernel."""
+    views = make_rig(w, h, D, seed=seed, channels=1)
+    wp, hp = w + 2 * D, h + 2 * D
+    pads = [oracle_lib.pad_replicate(v, D) for v in views]
+    t = oracle_lib.multistereo(pads, D, 0)
+    with sister_b200.Engine(w, h, D, n_slots=1) as eng:
+        eng.set_test_taps(True)
+        eng.compute(views, D, mode_mask=1)
+        lr = eng.fetch("lr_final", (4, wp * hp), np.int16)
+        masks = eng.fetch("masks", (4, hp, wp), np.uint8)
+    for v in range(4):
+        assert (lr[v] == t["lr"][v]).all(), f"median + LRC, view {v}: {(lr[v] != t['lr'][v]).sum()} px"
     assert (masks == t["masks"]).all()
 
 
