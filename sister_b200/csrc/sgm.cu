@@ -463,7 +463,7 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
 }
 
 template <int NR, int LPC, bool FULL, bool IL>
-__global__ void __launch_bounds__((sweep_warps_max(NR) + 1) * 32)
+__global__ void __launch_bounds__(NR <= 8 ? 1024 : (sweep_warps_max(NR) + 1) * 32) // (<= 64 registers: a block of another rig's match or fuse kernel fits beside a sweep block)
     k_sgm_sweeps(const uint8_t *__restrict__ fused, Dims d, SweepPlan pl, uint8_t *__restrict__ vols, uint8_t *__restrict__ mailbox, int *__restrict__ status, unsigned one)
 {
     constexpr int CPW = 32 / LPC;
