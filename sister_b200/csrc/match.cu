@@ -357,19 +357,26 @@ __global__ void __launch_bounds__(1024) k_median(const int16_t *__restrict__ wta
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
-// ---- the same recurrence with the warps running free behind each other (frames of 256 .. 2048 view columns, widths a
-// multiple of 4). In flat terms out[p] depends on out[p - w - 1 .. p - w + 1]: a column chunk of a row needs the same chunk
-// of the row above and one pixel of either neighbouring chunk -- not the whole row. So warp c owns the 128 columns
-// [128c, 128c + 128) (four pixels = two packed words per lane), walks down the rows, and waits only for its two neighbours
-// to have finished the row above (the first chunk's left neighbour is the last chunk two rows up, the last chunk's right
-// neighbour is the first chunk of the SAME row: the flat wrap-around of postprocess.cpp:31-67). No block barrier: a row
-// costs one neighbour hand-over (an mbarrier phase per warp and row, two barriers per warp alternating with the row parity
-// so that a waiter can never be two phases behind). The filtered row above stays in the lanes' registers; neighbouring
-// lanes exchange their edge pixels with shuffles, neighbouring warps through one boundary word per side and row in shared
-// memory (ring of 4 rows). Raw rows are streamed per warp with cp.async (kMed2Depth rows ahead) into the warp's own ring
-// of [32 x 2 words | left halo word | right halo word]. The row loop is bound by instruction issue (13 warps on one SM),
-// which is why a lane takes four pixels: the hand-over and the addressing are paid once per 128 columns.
-constexpr int kMed2Depth = 8, kMed2MaxWarps = 16, kMed2Slot = 264; // bytes of one raw row of a warp
+// ---- the same recurrence with the warps running free behind each other (padded frames of 256 .. 5120 columns). In flat
+// terms out[p] depends on out[p - w - 1 .. p - w + 1]: a column chunk of a row needs the same chunk of the row above and one
+// pixel of either neighbouring chunk -- not the whole row. So warp c owns the 64 K columns [64 K c, 64 K (c + 1)) (K packed
+// words = 2 K pixels per lane; K = 2 up to 2048 columns, K = 4 above), walks down the rows, and waits only for its two
+// neighbours to have finished the row above (the first chunk's left neighbour is the last chunk two rows up, the last
+// chunk's right neighbour is the first chunk of the SAME row: the flat wrap-around of postprocess.cpp:31-67). No block
+// barrier: a row costs one neighbour hand-over (an mbarrier phase per warp and row, two barriers per warp alternating with
+// the row parity so that a waiter can never be two phases behind). The filtered row above stays in the lanes' registers;
+// neighbouring lanes exchange their edge pixels with shuffles, neighbouring warps through one boundary word per side and
+// row in shared memory (ring of 4 rows). Raw rows are streamed per warp with cp.async (kMed2Depth rows ahead) into the
+// warp's own ring of [32 x K words | left halo word | right halo word].
+// What bounds it (measured with clock64 per phase, c2): a warp's row is ONE serial instruction stream -- about 120
+// instructions at 4-7 cycles each when a warp runs alone on its scheduler -- and the rows are serial; the hand-over itself
+// (arrive -> the neighbour's try_wait returns) is the smaller part. Hence four pixels per lane rather than two (26 warps
+// were slower than 13: the per-row overhead is per warp) and everything besides the median itself kept to a handful of
+// instructions: shared memory is addressed in its own window with offsets carried from row to row, the boundary loads and
+// stores are one instruction for the whole warp with per-lane addresses (no divergent branch), the two special rows are a
+// uniform branch.
+constexpr int kMed2Depth = 8, kMed2MaxWarps = 20;
+__host__ __device__ constexpr int med2_slot_bytes(int K) { return 32 * 4 * K + 16; } // one raw row of a warp: words, 2 halo words, pad
 
 __device__ __forceinline__ void med_mbar_init(unsigned a, int c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(c) : "memory"); }
 __device__ __forceinline__ void med_mbar_arrive(unsigned a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory"); }
@@ -391,41 +398,49 @@ __device__ __forceinline__ bool med_mbar_wait(unsigned a, unsigned parity)
 }
 
 __device__ __forceinline__ uint32_t med_lds32(unsigned a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ uint2 med_lds64(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void med_sts32(unsigned a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
+template <int K> __device__ __forceinline__ void med_lds_words(unsigned a, uint32_t (&w)[K])
+{
+    if constexpr (K == 2) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(w[0]), "=r"(w[1]) : "r"(a) : "memory");
+    else asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a) : "memory");
+}
+template <int K> __device__ __forceinline__ void med_stg_words(int16_t *g, const uint32_t (&w)[K])
+{
+    if constexpr (K == 2) *reinterpret_cast<uint2 *>(g) = make_uint2(w[0], w[1]);
+    else *reinterpret_cast<uint4 *>(g) = make_uint4(w[0], w[1], w[2], w[3]);
+}
 
-// grid 8 (one block per map), block 32 * ceil(max(wv) / 128). Everything a row needs besides the median itself is kept to a
-// handful of instructions -- a warp's row is one serial instruction sequence and the rows are serial: shared memory is
-// addressed in its own window with offsets carried from row to row, the boundary loads and stores are one instruction for
-// the whole warp with per-lane addresses (no divergent branch), and the two special rows are a uniform branch.
-__global__ void __launch_bounds__(32 * kMed2MaxWarps) k_median_chunks(const int16_t *__restrict__ wtaL, const int16_t *__restrict__ wtaR,
+// grid 8 (one block per map), block 32 * ceil(max(wv) / (64 K)), dynamic smem: barriers, boundary words, the warps' rings
+template <int K>
+__global__ void __launch_bounds__(K == 2 ? 512 : 32 * kMed2MaxWarps) k_median_chunks(const int16_t *__restrict__ wtaL, const int16_t *__restrict__ wtaR,
                                                                       Dims d, unsigned view_mask, int16_t *__restrict__ medL,
                                                                       int16_t *__restrict__ medR, int *__restrict__ status)
 {
-    __shared__ __align__(8) unsigned long long bars[2 * kMed2MaxWarps];          // [warp][row parity]
-    __shared__ __align__(8) uint32_t bnd[4][kMed2MaxWarps][2];                   // [row & 3][warp][first word, last word]
-    __shared__ __align__(16) unsigned char rings[kMed2MaxWarps * kMed2Depth * kMed2Slot];
+    constexpr int kSlot = med2_slot_bytes(K), kCols = 64 * K, kWin = 2 * K + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // [warp][row parity] barriers | [row & 3][warp][first word, last word] | rings
+    const unsigned bars_s = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned bnd_s = bars_s + 16u * kMed2MaxWarps;
+    constexpr unsigned kBndRow = 8u * kMed2MaxWarps;
     const int m = blockIdx.x, v = m >> 1;
     if (!((view_mask >> v) & 1u)) return;
     const int hv = view_rows(d, v), wv = view_cols(d, v);
-    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5, nch = (wv + 127) >> 7, L = nch - 1; // (the block is sized for the wider orientation)
-    const unsigned bars_s = (unsigned)__cvta_generic_to_shared(bars);
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5, nch = (wv + kCols - 1) / kCols, L = nch - 1; // (the block is sized for the wider orientation)
     if (threadIdx.x < 2 * nch) med_mbar_init(bars_s + 8u * threadIdx.x, 32);
     __syncthreads();
     if (c >= nch) return;
     const int N = hv * wv, p_lo = wv + 1, p_hi = N - wv - 5;
-    const int x = 128 * c + 4 * lane;                            // the lane's four columns x .. x + 3
-    const int nl = min(32, (wv - 128 * c) >> 2), last = nl - 1;  // lanes of this chunk that hold pixels (>= 2)
+    const int x = kCols * c + 2 * K * lane;                               // the lane's columns x .. x + 2K - 1
+    const int nl = min(32, (wv - kCols * c) / (2 * K)), last = nl - 1;    // lanes of this chunk that hold pixels (>= 2)
     const bool on = lane < nl, first_lane = lane == 0, last_lane = lane == last;
-    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(rings) + (unsigned)(c * (kMed2Depth * kMed2Slot));
-    const unsigned bnd_s = (unsigned)__cvta_generic_to_shared(bnd);
-    constexpr unsigned kRingBytes = kMed2Depth * kMed2Slot;
-    // ---- staging of the raw rows. Row j -> slot j % depth: 32 x (two words), then the word before the chunk and the word
-    // after it (flat neighbours, whatever row they belong to; nothing outside [0, N) is touched: the word before row 0 of
-    // chunk 0 and the word after the last row of the last chunk do not exist)
+    const unsigned ring_s = bnd_s + 4u * kBndRow + (unsigned)(c * (kMed2Depth * kSlot));
+    constexpr unsigned kRingBytes = kMed2Depth * kSlot;
+    // ---- staging of the raw rows. Row j -> slot j % depth: 32 x K words, then the word before the chunk and the word after
+    // it (flat neighbours, whatever row they belong to; nothing outside [0, N) is touched: the word before row 0 of chunk 0
+    // and the word after the last row of the last chunk do not exist)
     const char *gsrc = reinterpret_cast<const char *>(((m & 1) ? wtaR : wtaL) + (size_t)v * d.px + x);
-    const int halo_src = first_lane ? -4 : 8;
-    const unsigned own_dst = 8u * lane, halo_dst = first_lane ? 256u : 260u;
+    const int halo_src = first_lane ? -4 : 4 * K;
+    const unsigned own_dst = 4u * K * lane, halo_dst = 128u * K + (first_lane ? 0u : 4u);
     const unsigned halo_rd = (first_lane || last_lane) ? halo_dst : own_dst; // (the other lanes do not use what they read here)
     const int halo_j0 = first_lane ? (c == 0 ? 1 : 0) : (last_lane ? 0 : hv);           // rows [halo_j0, halo_j1] have the halo word
     const int halo_j1 = (last_lane && !first_lane && c == L) ? hv - 2 : hv - 1;
@@ -434,27 +449,35 @@ __global__ void __launch_bounds__(32 * kMed2MaxWarps) k_median_chunks(const int1
     int st_j = 0;
     auto stage = [&]() {
         if (st_j < hv) {
-            if (on) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(ring_s + st_off + own_dst), "l"(gsrc) : "memory");
+            if (on) {
+                if constexpr (K == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(ring_s + st_off + own_dst), "l"(gsrc) : "memory");
+                else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(ring_s + st_off + own_dst), "l"(gsrc) : "memory");
+            }
             if (st_j >= halo_j0 && st_j <= halo_j1)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(ring_s + st_off + halo_dst), "l"(gsrc + halo_src) : "memory");
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         gsrc += row_bytes;
         st_j++;
-        st_off += kMed2Slot;
+        st_off += kSlot;
         if (st_off == kRingBytes) st_off = 0;
     };
-    // the five window words of the raw row in slot offset rd for this lane: (x-1 x) (x x+1) (x+1 x+2) (x+2 x+3) (x+3 x+4)
+    // the window words of the next raw row for this lane: (x-1 x) (x x+1) (x+1 x+2) ... (x+2K-1 x+2K)
     unsigned rd_off = 0;
-    auto raw_row = [&](uint32_t (&w)[5]) {
-        const uint2 own = med_lds64(ring_s + rd_off + own_dst);
+    auto raw_row = [&](uint32_t (&w)[kWin]) {
+        uint32_t own[K];
+        med_lds_words<K>(ring_s + rd_off + own_dst, own);
         const uint32_t halo = med_lds32(ring_s + rd_off + halo_rd);
-        uint32_t left = __shfl_up_sync(0xFFFFFFFFu, own.y, 1), right = __shfl_down_sync(0xFFFFFFFFu, own.x, 1);
+        uint32_t left = __shfl_up_sync(0xFFFFFFFFu, own[K - 1], 1), right = __shfl_down_sync(0xFFFFFFFFu, own[0], 1);
         if (first_lane) left = halo;
         if (last_lane) right = halo;
-        w[0] = __byte_perm(left, own.x, 0x5432); w[1] = own.x; w[2] = __byte_perm(own.x, own.y, 0x5432); w[3] = own.y;
-        w[4] = __byte_perm(own.y, right, 0x5432);
-        rd_off += kMed2Slot;
+        w[0] = __byte_perm(left, own[0], 0x5432);
+#pragma unroll
+        for (int i = 0; i < K; i++) {
+            w[2 * i + 1] = own[i];
+            w[2 * i + 2] = __byte_perm(own[i], i + 1 < K ? own[i + 1 < K ? i + 1 : i] : right, 0x5432);
+        }
+        rd_off += kSlot;
         if (rd_off == kRingBytes) rd_off = 0;
     };
     // ---- hand-over with the neighbouring warps. Left: warp c - 1 at row r - 1 (chunk 0: the last chunk at row r - 2);
@@ -469,14 +492,16 @@ __global__ void __launch_bounds__(32 * kMed2MaxWarps) k_median_chunks(const int1
 
     for (int j = 0; j < kMed2Depth - 1; j++) stage();
     bool broken = false;
-    uint32_t q[5], s[5] = {0u, 0u, 0u, 0u, 0u};
-    uint32_t f0, f1; // this lane's part of the finished row above
+    uint32_t q[kWin], s[kWin], f[K]; // raw row r, raw row r + 1, this lane's part of the finished row above
+#pragma unroll
+    for (int k = 0; k < kWin; k++) s[k] = 0u;
     // row 0 is copied unchanged
     asm volatile("cp.async.wait_group %0;\n" ::"n"(kMed2Depth - 2) : "memory");
     raw_row(q);
-    f0 = q[1]; f1 = q[3];
-    if (on) *reinterpret_cast<uint2 *>(gout) = make_uint2(f0, f1);
-    if (bnd_writer) med_sts32(my_bnd, first_lane ? f0 : f1);
+#pragma unroll
+    for (int i = 0; i < K; i++) f[i] = q[2 * i + 1];
+    if (on) med_stg_words<K>(gout, f);
+    if (bnd_writer) med_sts32(my_bnd, first_lane ? f[0] : f[K - 1]);
     med_mbar_arrive(bars_s + 8u * (2 * c));
     stage();
     asm volatile("cp.async.wait_group %0;\n" ::"n"(kMed2Depth - 2) : "memory");
@@ -486,8 +511,10 @@ __global__ void __launch_bounds__(32 * kMed2MaxWarps) k_median_chunks(const int1
         gout += wv;
         asm volatile("cp.async.wait_group %0;\n" ::"n"(kMed2Depth - 2) : "memory"); // rows <= r + 1 have landed
         if (r + 1 < hv) raw_row(s);
-        uint32_t fl = __shfl_up_sync(0xFFFFFFFFu, f1, 1), fr = __shfl_down_sync(0xFFFFFFFFu, f0, 1);
-        uint32_t v0 = q[1], v1 = q[3];
+        uint32_t fl = __shfl_up_sync(0xFFFFFFFFu, f[K - 1], 1), fr = __shfl_down_sync(0xFFFFFFFFu, f[0], 1);
+        uint32_t val[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) val[i] = q[2 * i + 1];
         if (r < hv - 1) {
             // the row above: this chunk is in the registers; one pixel of either neighbouring chunk
             if (!broken) {
@@ -500,39 +527,54 @@ __global__ void __launch_bounds__(32 * kMed2MaxWarps) k_median_chunks(const int1
                     if (lane == 0) atomicOr(status, kStatusSpinTimeout);
                 }
             }
-            const uint32_t edge = med_lds32(b_base + 128u * ((unsigned)(r - b_delta) & 3u)); // (row 1, chunk 0, lane 0: unused, out[w] = 0)
+            const uint32_t edge = med_lds32(b_base + kBndRow * ((unsigned)(r - b_delta) & 3u)); // (row 1, chunk 0, lane 0: unused, out[w] = 0)
             if (first_lane) fl = edge;
             if (last_lane) fr = edge;
-            uint32_t l[5], md[5], h[5];
-            sort3p(__byte_perm(fl, f0, 0x5432), q[0], s[0], l[0], md[0], h[0]);
-            sort3p(f0, q[1], s[1], l[1], md[1], h[1]);
-            sort3p(__byte_perm(f0, f1, 0x5432), q[2], s[2], l[2], md[2], h[2]);
-            sort3p(f1, q[3], s[3], l[3], md[3], h[3]);
-            sort3p(__byte_perm(f1, fr, 0x5432), q[4], s[4], l[4], md[4], h[4]);
-            v0 = med3p(__vimax3_s16x2(l[0], l[1], l[2]), med3p(md[0], md[1], md[2]), __vimin3_s16x2(h[0], h[1], h[2]));
-            v1 = med3p(__vimax3_s16x2(l[2], l[3], l[4]), med3p(md[2], md[3], md[4]), __vimin3_s16x2(h[2], h[3], h[4]));
+            uint32_t l[kWin], md[kWin], h[kWin];
+            sort3p(__byte_perm(fl, f[0], 0x5432), q[0], s[0], l[0], md[0], h[0]);
+#pragma unroll
+            for (int i = 0; i < K; i++) {
+                sort3p(f[i], q[2 * i + 1], s[2 * i + 1], l[2 * i + 1], md[2 * i + 1], h[2 * i + 1]);
+                sort3p(__byte_perm(f[i], i + 1 < K ? f[i + 1 < K ? i + 1 : i] : fr, 0x5432), q[2 * i + 2], s[2 * i + 2], l[2 * i + 2], md[2 * i + 2], h[2 * i + 2]);
+            }
+#pragma unroll
+            for (int i = 0; i < K; i++)
+                val[i] = med3p(__vimax3_s16x2(l[2 * i], l[2 * i + 1], l[2 * i + 2]), med3p(md[2 * i], md[2 * i + 1], md[2 * i + 2]),
+                               __vimin3_s16x2(h[2 * i], h[2 * i + 1], h[2 * i + 2]));
             if (r == 1 || r == hv - 2) { // the first and the last filtered positions: postprocess.cpp:29,61-63
                 const int base = r * wv + x;
-                auto fix = [&](uint32_t val, uint32_t rawv, int p) -> uint32_t {
-                    if (p == wv) val &= 0xFFFF0000u;                                   // out[w] = 0
-                    else if (p < p_lo || p > p_hi) val = (val & 0xFFFF0000u) | (rawv & 0xFFFFu);
-                    if (p + 1 < p_lo || p + 1 > p_hi) val = (val & 0xFFFFu) | (rawv & 0xFFFF0000u);
-                    return val;
-                };
-                v0 = fix(v0, q[1], base);
-                v1 = fix(v1, q[3], base + 2);
+#pragma unroll
+                for (int i = 0; i < K; i++) {
+                    const int p = base + 2 * i;
+                    const uint32_t rawv = q[2 * i + 1];
+                    if (p == wv) val[i] &= 0xFFFF0000u;                                   // out[w] = 0
+                    else if (p < p_lo || p > p_hi) val[i] = (val[i] & 0xFFFF0000u) | (rawv & 0xFFFFu);
+                    if (p + 1 < p_lo || p + 1 > p_hi) val[i] = (val[i] & 0xFFFFu) | (rawv & 0xFFFF0000u);
+                }
             }
         }
-        f0 = v0; f1 = v1;
-        if (bnd_writer) med_sts32(my_bnd + 128u * ((unsigned)r & 3u), first_lane ? f0 : f1);
+#pragma unroll
+        for (int i = 0; i < K; i++) f[i] = val[i];
+        if (bnd_writer) med_sts32(my_bnd + kBndRow * ((unsigned)r & 3u), first_lane ? f[0] : f[K - 1]);
         // (the last row has no dependencies and nobody waits for it: arriving for it could put this warp two phases ahead
         // of a neighbour that still waits for row hv - 3 on the same barrier)
         if (r < hv - 1) med_mbar_arrive(bars_s + 8u * (2 * c + (r & 1)));
-        if (on) *reinterpret_cast<uint2 *>(gout) = make_uint2(f0, f1);
+        if (on) med_stg_words<K>(gout, f);
 #pragma unroll
-        for (int k = 0; k < 5; k++) q[k] = s[k];
+        for (int k = 0; k < kWin; k++) q[k] = s[k];
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int K>
+static void launch_median_chunks(const int16_t *wtaL, const int16_t *wtaR, const Dims &d, unsigned view_mask, int16_t *medL, int16_t *medR,
+                                 int *status, int m, cudaStream_t st, LaunchCounter &lc)
+{
+    const int warps = (m + 64 * K - 1) / (64 * K);
+    const size_t smem = (size_t)16 * kMed2MaxWarps + (size_t)4 * 8 * kMed2MaxWarps + (size_t)warps * kMed2Depth * med2_slot_bytes(K);
+    if (smem > 48 * 1024) lc.fail(optin_dynamic_smem((const void *)k_median_chunks<K>, smem));
+    k_median_chunks<K><<<8, 32 * warps, smem, st>>>(wtaL, wtaR, d, view_mask, medL, medR, status);
+    lc.add();
 }
 
 // grid (ceil(wv/256), max(hv), 4), block 256
@@ -563,11 +605,12 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
 {
     int m = d.Wp > d.Hp ? d.Wp : d.Hp;
     const int lo = d.Wp < d.Hp ? d.Wp : d.Hp;
-    if (lo >= 256 && m <= 128 * kMed2MaxWarps && d.Wp % 8 == 0 && d.Hp % 8 == 0) {
-        // warps free-running behind each other, one per 128 columns; the block is sized for the wider of the two frame
-        // orientations and the warps a narrower map does not need leave at once
-        k_median_chunks<<<8, 32 * ((m + 127) / 128), 0, st>>>(wtaL, wtaR, d, view_mask, medL, medR, status);
-        lc.add();
+    // warps free-running behind each other, one per 128 (256) columns; the block is sized for the wider of the two frame
+    // orientations and the warps a narrower map does not need leave at once
+    if (lo >= 256 && m <= 2048 && d.Wp % 8 == 0 && d.Hp % 8 == 0) {
+        launch_median_chunks<2>(wtaL, wtaR, d, view_mask, medL, medR, status, m, st, lc);
+    } else if (lo >= 512 && m <= 256 * kMed2MaxWarps && d.Wp % 16 == 0 && d.Hp % 16 == 0) {
+        launch_median_chunks<4>(wtaL, wtaR, d, view_mask, medL, medR, status, m, st, lc);
     } else {
         const size_t med_smem = (size_t)(kMedRing + 4) * m * sizeof(int16_t);
         lc.fail(optin_dynamic_smem((const void *)k_median, med_smem));

@@ -80,12 +80,13 @@ def test_every_stage_against_oracle(engine, oracle_lib, w, h, D, kind, seed, col
     assert (masks == t["masks"]).all()
 
 
-@pytest.mark.parametrize("w,h,D,seed", [(240, 240, 8, 31), (248, 240, 8, 32), (376, 248, 8, 33), (1000, 264, 16, 34), (252, 244, 8, 35)])
+@pytest.mark.parametrize("w,h,D,seed", [(240, 240, 8, 31), (248, 240, 8, 32), (376, 248, 8, 33), (1000, 264, 16, 34), (252, 244, 8, 35), (2080, 496, 8, 36)])
 def test_median_kernels_by_frame_shape(oracle_lib, w, h, D, seed):
     """The recursive median (postprocess.cpp:31-67) has two kernels: warps chained by neighbour hand-over (128 columns each) for
     padded frames of 256 .. 2048 with sides a multiple of 8, one block barrier per row otherwise. Shapes: exactly two chunks,
-    a last chunk of two lanes (264 = 2 * 128 + 8), different chunk counts for the two orientations, nine chunks, and one
-    shape (268 x 260: multiples of 4, not of 8) that takes the barrier kernel."""
+    a last chunk of two lanes (264 = 2 * 128 + 8), different chunk counts for the two orientations, nine chunks, one
+    shape (268 x 260: multiples of 4, not of 8) that takes the barrier kernel, and one wider than 2048 (2096 x 512: eight pixels per
+    lane, a last chunk of six lanes)."""
     views = make_rig(w, h, D, seed=seed, channels=1)
     wp, hp = w + 2 * D, h + 2 * D
     pads = [oracle_lib.pad_replicate(v, D) for v in views]
