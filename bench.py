@@ -517,6 +517,15 @@ def run_bands(ctx: Dist, args, reps=2, check=True):
             if rep > 0:
                 times.append(dt * 1e3)
         full = gather_band_rows(rows, d, h, hp, dst=0) if ctx.world > 1 else rows
+        timeline = None
+        if ctx.world > 1:  # one more frame with the device drained after every phase: where the time of a banded frame goes
+            trace = []
+            ctx.barrier()
+            compute_banded(worker, ctx.world, ctx.rank, trace=trace)
+            mine = [[label, round(t * 1e3, 2)] for label, t in trace]
+            allt = [None] * ctx.world
+            ctx.dist.all_gather_object(allt, mine)
+            timeline = {f"rank{r}": t for r, t in enumerate(allt)}
         equal, single_ms = None, None
         if check and ctx.rank == 0:
             eng.compute(views, d, mode_mask=1)
@@ -527,7 +536,8 @@ def run_bands(ctx: Dist, args, reps=2, check=True):
     ms = statistics.median(times)
     return {"what": "one frame by row bands, exact state hand-over between the bands (NCCL send/recv)", "shape": [w, h, d], "n_gpus": ctx.world,
             "ms_per_frame": ms, "frames_per_s": 1e3 / ms, "gcost_evals_per_s": cost_evals(w, h, d) / ms / 1e6,
-            "single_gpu_host_call_ms": single_ms, "equal_to_single_gpu": equal}
+            "single_gpu_host_call_ms": single_ms, "equal_to_single_gpu": equal,
+            "wta_rows_shared": ctx.world > 1, "timeline_ms_end_of_phase": timeline}
 
 
 def main():

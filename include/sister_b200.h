@@ -149,6 +149,15 @@ int sister_stereo(sister_ctx *ctx, const uint8_t *center, const uint8_t *side, i
  *                         uint16 map of which only the band's rows are written
  * All three only enqueue on the slot's stream; sister_sync(slot) completes them. Outputs are bit-identical to
  * sister_compute on one GPU (tests/test_bands_gpu.py).
+ *
+ * The raw-cost WTA (census.cpp:63-88 + postprocess.cpp:103-141 for both maps of every view) is the largest of the stages a
+ * band would otherwise repeat for the whole frame, and its rows are independent, so n bands can share it:
+ *   sister_band_submit_share  like sister_band_submit up to the WTA, but only for the rows [hv * share / n, hv * (share + 1) / n)
+ *                             of every view (hv: the view frame's rows); the results are packed into share_out_dev,
+ *                             sister_band_share_bytes() of device memory (the same size for every share)
+ *   (the caller all-gathers the n shares, in share order, into one buffer of n * sister_band_share_bytes())
+ *   sister_band_submit_rest   unpacks the gathered shares into the slot's maps, then the masks and the band's fused cost:
+ *                             the slot is where sister_band_submit would have left it
  */
 size_t sister_band_state_bytes(int w, int h, int disp_count);
 /* A context for row bands only: like sister_create, but the volumes of a slot -- the fused cost and the four SGM pair
@@ -159,6 +168,11 @@ size_t sister_band_state_bytes(int w, int h, int disp_count);
 int sister_create_band(sister_ctx **ctx, int device, int max_w, int max_h, int max_disp, int n_slots, int max_band_rows);
 int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h, int channels,
                        int disp_count, int mode, int band_row0, int band_row1);
+size_t sister_band_share_bytes(int w, int h, int disp_count, int n_shares);
+int sister_band_submit_share(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h, int channels,
+                             int disp_count, int mode, int band_row0, int band_row1, int share, int n_shares,
+                             uint8_t *share_out_dev);
+int sister_band_submit_rest(sister_ctx *ctx, int slot, const uint8_t *shares_dev, int n_shares);
 int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *state_in_dev, uint8_t *state_out_dev);
 int sister_band_finish(sister_ctx *ctx, int slot, uint16_t *out_dev);
 

@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "sister_submit_device", "sister_sync", "sister_dev_alloc", "sister_dev_free", "sister_host_alloc", "sister_host_free", "sister_dev_upload",
     "sister_dev_download", "sister_set_profiling", "sister_region_begin", "sister_region_end", "sister_get_stage_ms", "sister_get_stage_launches",
     "sister_get_launch_count", "sister_debug_fetch", "sister_set_test_taps", "sister_set_full_frame",
-    "sister_stereo", "sister_create_band", "sister_band_state_bytes", "sister_band_submit", "sister_band_vertical", "sister_band_finish", "sister_test_sgm", "sister_strerror", "sister_last_error",
+    "sister_stereo", "sister_create_band", "sister_band_state_bytes", "sister_band_submit", "sister_band_share_bytes", "sister_band_submit_share", "sister_band_submit_rest", "sister_band_vertical", "sister_band_finish", "sister_test_sgm", "sister_strerror", "sister_last_error",
     "sister_version",
 )
 
@@ -114,6 +114,13 @@ def load_library():
     L.sister_band_state_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     L.sister_band_submit.restype = C.c_int
     L.sister_band_submit.argtypes = [vp, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.sister_band_share_bytes.restype = C.c_size_t
+    L.sister_band_share_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.sister_band_submit_share.restype = C.c_int
+    L.sister_band_submit_share.argtypes = [vp, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, vp]
+    L.sister_band_submit_rest.restype = C.c_int
+    L.sister_band_submit_rest.argtypes = [vp, C.c_int, vp, C.c_int]
     L.sister_band_vertical.restype = C.c_int
     L.sister_band_vertical.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.sister_band_finish.restype = C.c_int
@@ -303,6 +310,20 @@ class Engine:
         vb = w * h * channels
         varr = (C.c_void_p * 5)(*[C.c_void_p(rig_ptr + k * vb) for k in range(5)])
         self._chk(self.lib.sister_band_submit(self.ctx, slot, varr, w, h, channels, disp_count, mode, row0, row1))
+
+    def band_share_bytes(self, w: int, h: int, disp_count: int, n_shares: int) -> int:
+        return int(self.lib.sister_band_share_bytes(w, h, disp_count, n_shares))
+
+    def band_submit_share(self, slot: int, rig_ptr: int, w: int, h: int, channels: int, disp_count: int, mode: int, row0: int, row1: int,
+                          share: int, n_shares: int, share_out_ptr: int):
+        """Staging, census and this share of the raw-cost WTA rows (packed into share_out_ptr); band_submit_rest continues."""
+        vb = w * h * channels
+        varr = (C.c_void_p * 5)(*[C.c_void_p(rig_ptr + k * vb) for k in range(5)])
+        self._chk(self.lib.sister_band_submit_share(self.ctx, slot, varr, w, h, channels, disp_count, mode, row0, row1, share, n_shares,
+                                                    C.c_void_p(share_out_ptr)))
+
+    def band_submit_rest(self, slot: int, shares_ptr: int, n_shares: int):
+        self._chk(self.lib.sister_band_submit_rest(self.ctx, slot, C.c_void_p(shares_ptr), n_shares))
 
     def band_vertical(self, slot: int, pass_: int, state_in_ptr: int, state_out_ptr: int):
         self._chk(self.lib.sister_band_vertical(self.ctx, slot, pass_, C.c_void_p(state_in_ptr) if state_in_ptr else None,

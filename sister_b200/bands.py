@@ -1,8 +1,11 @@
 """Row-band sharding of ONE large frame over the GPUs of one box (BASELINE.json configs[3]).
 
 Each rank owns a contiguous band of rows of the PADDED frame. The volumes (fused cost, four SGM pair volumes, final sum)
-are filled for the band only -- and, in an Engine made with max_band_rows, allocated for it only; staging, census, raw-cost
-WTA and masks are recomputed for the whole frame by every rank (include/sister_b200.h, "Row bands"). Every sweep of the
+are filled for the band only -- and, in an Engine made with max_band_rows, allocated for it only. Staging, census and the
+masks are recomputed for the whole frame by every rank; the raw-cost WTA, the largest of the whole-frame stages, is shared:
+every rank matches 1/G of each view's rows and the packed int16 maps are all-gathered (include/sister_b200.h, "Row bands";
+a worker without share_match -- the numpy stand-in of the CPU tests, or EngineBandWorker(share_match=False) -- computes the
+whole frame itself). Every sweep of the
 aggregation carries a diagonal path, so all of it crosses the bands: pass 0 flows from rank 0 down to rank G-1, pass 1
 from rank G-1 up to rank 0, and each rank continues from the state its neighbour left (band_state_bytes per pass, exact --
 no approximate overlapping halos). While rank t works on pass 0, rank G-1-t works on pass 1, so the two wavefronts
@@ -87,18 +90,43 @@ def simulate_programs(world: int) -> int:
     return steps
 
 
-def compute_banded(worker, world: int, rank: int, group=None):
+def compute_banded(worker, world: int, rank: int, group=None, trace=None):
     """Run this rank's band. `worker` provides
          submit()                              -- whole-frame stages and the fused cost of the band
+         submit_share(rank, world) / submit_rest(gathered, world)   -- the same with the raw-cost WTA shared between the
+                                                  ranks (used when worker.share_match is set)
          vertical(pass, state_in, want_out)    -- the four paths of one pass inside the band; state_in / return value are torch
                                                   uint8 tensors on the worker's device (or None)
          new_state()                           -- an empty state tensor to receive into
          finish()                              -- final WTA; returns this band's rows of the H x W map (torch int16 tensor
                                                   holding the uint16 bits, possibly 0 rows)
+    trace: a list that receives (label, seconds since the call) after each phase has COMPLETED on the device (the worker is
+    drained after every phase, so a traced run is a little slower than an untraced one).
     Returns the band's rows."""
+    import time
+
     import torch.distributed as dist
 
-    worker.submit()
+    t_start = time.perf_counter()
+
+    def mark(label):
+        if trace is not None:
+            worker.drain()
+            trace.append((label, time.perf_counter() - t_start))
+
+    if world > 1 and getattr(worker, "share_match", False):
+        import torch
+
+        share = worker.submit_share(rank, world)          # this rank's rows of every view's WTA maps, packed
+        mark("stage+census+match share")
+        gathered = torch.empty(world * share.numel(), dtype=share.dtype, device=share.device)
+        dist.all_gather_into_tensor(gathered, share, group=group)
+        mark("all-gather WTA maps")
+        worker.submit_rest(gathered, world)
+        mark("masks+fuse band")
+    else:
+        worker.submit()
+        mark("stage+census+match+masks+fuse band")
     inbox = {}
     outbox = {}
     for kind, p, peer in band_program(world, rank):
@@ -106,13 +134,18 @@ def compute_banded(worker, world: int, rank: int, group=None):
             buf = worker.new_state()
             dist.recv(buf, src=peer, group=group)
             inbox[p] = buf
+            mark(f"recv state pass {p}")
         elif kind == "compute":
             src = rank - 1 if p == 0 else rank + 1
             dst = rank + 1 if p == 0 else rank - 1
             outbox[p] = worker.vertical(p, inbox.get(p) if 0 <= src < world else None, 0 <= dst < world)
+            mark(f"sweeps pass {p}")
         else:
             dist.send(outbox[p], dst=peer, group=group)
-    return worker.finish()
+            mark(f"send state pass {p}")
+    rows = worker.finish()
+    mark("final sum+WTA")
+    return rows
 
 
 def run_bands_in_process(workers):
@@ -120,8 +153,15 @@ def run_bands_in_process(workers):
     This is how the tests run G bands on one GPU (one slot per band; with an Engine(max_band_rows=...) the G slots together
     hold one frame's worth of volumes). Returns the list of the bands' rows."""
     world = len(workers)
-    for w in workers:
-        w.submit()
+    if world > 1 and all(getattr(w, "share_match", False) for w in workers):
+        import torch
+
+        gathered = torch.cat([w.submit_share(r, world) for r, w in enumerate(workers)])
+        for w in workers:
+            w.submit_rest(gathered, world)
+    else:
+        for w in workers:
+            w.submit()
     progs = [band_program(world, r) for r in range(world)]
     pc = [0] * world
     inbox = [dict() for _ in range(world)]
@@ -181,7 +221,7 @@ def gather_band_rows(local_rows, D: int, H: int, hp: int, dst: int = 0, group=No
 class EngineBandWorker:
     """The band worker on the GPU box: drives sister_band_* of one Engine (one context on this rank's GPU)."""
 
-    def __init__(self, engine, views, disp_count: int, rank: int, world: int, mode: int = 0, slot: int = 0):
+    def __init__(self, engine, views, disp_count: int, rank: int, world: int, mode: int = 0, slot: int = 0, share_match: bool = True):
         import torch
 
         self.torch = torch
@@ -192,6 +232,7 @@ class EngineBandWorker:
         self.D = disp_count
         self.mode = mode
         self.slot = slot
+        self.share_match = share_match
         self.hp = self.h + 2 * disp_count
         self.row0, self.row1 = band_rows(self.hp, world, rank)
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -205,6 +246,20 @@ class EngineBandWorker:
     def submit(self):
         self.eng.band_submit(self.slot, self.rig, self.w, self.h, self.ch, self.D, self.mode, self.row0, self.row1)
 
+    def submit_share(self, share: int, n_shares: int):
+        """Whole-frame staging and census, this share of the WTA rows; returns the packed maps (uint8 tensor, complete)."""
+        nbytes = self.eng.band_share_bytes(self.w, self.h, self.D, n_shares)
+        out = self.torch.zeros(nbytes, dtype=self.torch.uint8, device=self.device)
+        self.torch.cuda.current_stream().synchronize()  # (the zero fill runs on torch's stream, the library on its own)
+        self.eng.band_submit_share(self.slot, self.rig, self.w, self.h, self.ch, self.D, self.mode, self.row0, self.row1, share, n_shares,
+                                   out.data_ptr())
+        self.eng.sync(self.slot)
+        return out
+
+    def submit_rest(self, gathered, n_shares: int):
+        self.torch.cuda.current_stream().synchronize()  # the gathered shares were written on torch's stream
+        self.eng.band_submit_rest(self.slot, gathered.data_ptr(), n_shares)
+
     def vertical(self, p: int, state_in, want_out: bool):
         out = self.new_state() if want_out else None
         if state_in is not None:
@@ -213,6 +268,10 @@ class EngineBandWorker:
         if want_out:
             self.eng.sync(self.slot)  # the library runs on its own stream: the state must be complete before it is sent
         return out
+
+    def drain(self):
+        self.eng.sync(self.slot)
+        self.torch.cuda.synchronize()
 
     def finish(self):
         self.eng.band_finish(self.slot, self.out.data_ptr())

@@ -457,8 +457,32 @@ size_t sister_band_state_bytes(int w, int h, int disp_count)
     return sgm_band_state_bytes(d);
 }
 
-int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h, int channels, int disp_count, int mode,
-                       int band_row0, int band_row1)
+// the packed WTA maps of one share: map i = 2 * view + (0 left, 1 right), each with room for ceil(hv / n) rows
+static size_t band_share_layout(const Dims &d, int n, size_t off[9])
+{
+    size_t o = 0;
+    for (int i = 0; i < 8; i++) {
+        const int v = i >> 1, hv = view_rows(d, v), wv = view_cols(d, v);
+        off[i] = o;
+        o += (size_t)((hv + n - 1) / n) * wv * sizeof(int16_t);
+    }
+    off[8] = o;
+    return o;
+}
+
+size_t sister_band_share_bytes(int w, int h, int disp_count, int n_shares)
+{
+    if (w <= 0 || h <= 0 || disp_count <= 0 || n_shares <= 0) return 0;
+    Dims d;
+    d.W = w; d.H = h; d.D = disp_count; d.Wp = w + 2 * disp_count; d.Hp = h + 2 * disp_count;
+    d.px = (long long)d.Wp * d.Hp;
+    size_t off[9];
+    return band_share_layout(d, n_shares, off);
+}
+
+// validation + staging + census; the slot remembers the band
+static int band_begin(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h, int channels, int disp_count, int mode,
+                      int band_row0, int band_row1)
 {
     int rc = slot_ok(ctx, slot);
     if (rc) return rc;
@@ -475,27 +499,90 @@ int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev
     for (int k = 2; k < 5; k++)
         if (views_dev[k] - views_dev[k - 1] != stride) { ctx->err = "device views must be equally spaced"; return SISTER_E_ARG; }
     if (stride <= 0) { ctx->err = "device views must be in ascending address order"; return SISTER_E_ARG; }
-    const unsigned vm = mode == 0 ? 0xFu : mode == 1 ? 0x3u : 0xCu; // hpp:262-276
-    // staging, census, raw-cost WTA and the masks need neighbours far outside the band (D rows for the vertical views,
-    // the whole map for the recursive median): every band computes them for the whole frame; the volumes -- fused cost,
-    // path bytes, i.e. all the memory and most of the time -- exist for the band's rows only
     launch_prep(views_dev[0], (size_t)stride, w * channels, channels, d, s.d_oriented, s.st, ctx->lc);
     launch_census(s.d_oriented, d, s.d_census, s.st, ctx->lc);
-    launch_match_wta(s.d_census, d, vm, s.d_wtaL, s.d_wtaR, s.st, ctx->lc);
-    launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, vm, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.d_status, s.st, ctx->lc);
-    // a band context's volumes start with the band's first row: every kernel addresses rows of the padded frame, so the
-    // bases are moved back by the rows that are not there (only the band's rows are ever touched)
-    s.sgm.row_shift = ctx->band_rows > 0 ? (size_t)band_row0 * (size_t)d.Wp * (size_t)d.D : 0;
-    launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused - s.sgm.row_shift, s.d_status, s.st, ctx->lc, band_row0, band_row1);
-    s.last_fused = s.d_fused;
-    SCK(cudaGetLastError());
-    SCK(take_launch_error(ctx));
     s.dims = d;
     s.mode_mask = 1u << mode;
     s.full_frame = false;
     s.band_r0 = band_row0; s.band_r1 = band_row1;
     s.host_io = false;
     return SISTER_OK;
+}
+
+// masks (whole frame) + the band's fused cost, from the WTA maps in the slot
+static int band_rest(sister_ctx *ctx, Slot &s)
+{
+    const Dims &d = s.dims;
+    const unsigned vm = s.mode_mask == 1u ? 0xFu : s.mode_mask == 2u ? 0x3u : 0xCu; // hpp:262-276
+    launch_median_lrc_mask(s.d_wtaL, s.d_wtaR, d, vm, s.d_medL, s.d_medR, s.d_lr, s.d_masks, s.d_status, s.st, ctx->lc);
+    // a band context's volumes start with the band's first row: every kernel addresses rows of the padded frame, so the
+    // bases are moved back by the rows that are not there (only the band's rows are ever touched)
+    s.sgm.row_shift = ctx->band_rows > 0 ? (size_t)s.band_r0 * (size_t)d.Wp * (size_t)d.D : 0;
+    launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused - s.sgm.row_shift, s.d_status, s.st, ctx->lc, s.band_r0, s.band_r1);
+    s.last_fused = s.d_fused;
+    SCK(cudaGetLastError());
+    SCK(take_launch_error(ctx));
+    return SISTER_OK;
+}
+
+int sister_band_submit(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h, int channels, int disp_count, int mode,
+                       int band_row0, int band_row1)
+{
+    // staging, census, raw-cost WTA and the masks need neighbours far outside the band (D rows for the vertical views,
+    // the whole map for the recursive median): every band computes them for the whole frame; the volumes -- fused cost,
+    // path bytes, i.e. all the memory and most of the time -- exist for the band's rows only
+    int rc = band_begin(ctx, slot, views_dev, w, h, channels, disp_count, mode, band_row0, band_row1);
+    if (rc) return rc;
+    Slot &s = ctx->slots[slot];
+    const unsigned vm = mode == 0 ? 0xFu : mode == 1 ? 0x3u : 0xCu;
+    launch_match_wta(s.d_census, s.dims, vm, s.d_wtaL, s.d_wtaR, s.st, ctx->lc);
+    return band_rest(ctx, s);
+}
+
+int sister_band_submit_share(sister_ctx *ctx, int slot, const uint8_t *const views_dev[5], int w, int h, int channels, int disp_count,
+                             int mode, int band_row0, int band_row1, int share, int n_shares, uint8_t *share_out_dev)
+{
+    if (n_shares <= 0 || share < 0 || share >= n_shares || !share_out_dev) { if (ctx) ctx->err = "0 <= share < n_shares and a share buffer are required"; return SISTER_E_ARG; }
+    int rc = band_begin(ctx, slot, views_dev, w, h, channels, disp_count, mode, band_row0, band_row1);
+    if (rc) return rc;
+    Slot &s = ctx->slots[slot];
+    const Dims &d = s.dims;
+    const unsigned vm = mode == 0 ? 0xFu : mode == 1 ? 0x3u : 0xCu;
+    launch_match_wta(s.d_census, d, vm, s.d_wtaL, s.d_wtaR, s.st, ctx->lc, share, n_shares);
+    size_t off[9];
+    band_share_layout(d, n_shares, off);
+    for (int i = 0; i < 8; i++) {
+        const int v = i >> 1, hv = view_rows(d, v), wv = view_cols(d, v);
+        if (!((vm >> v) & 1u)) continue;
+        const int r0 = share_row0(hv, share, n_shares), r1 = share_row0(hv, share + 1, n_shares);
+        const int16_t *src = ((i & 1) ? s.d_wtaR : s.d_wtaL) + (size_t)v * d.px + (size_t)r0 * wv;
+        if (r1 > r0) SCK(cudaMemcpyAsync(share_out_dev + off[i], src, (size_t)(r1 - r0) * wv * sizeof(int16_t), cudaMemcpyDeviceToDevice, s.st));
+    }
+    SCK(cudaGetLastError());
+    SCK(take_launch_error(ctx));
+    return SISTER_OK;
+}
+
+int sister_band_submit_rest(sister_ctx *ctx, int slot, const uint8_t *shares_dev, int n_shares)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    Slot &s = ctx->slots[slot];
+    if (!shares_dev || n_shares <= 0 || s.band_r1 <= s.band_r0) { ctx->err = "sister_band_submit_share first; the gathered shares must not be null"; return SISTER_E_ARG; }
+    SCK(cudaSetDevice(ctx->device));
+    const Dims &d = s.dims;
+    const unsigned vm = s.mode_mask == 1u ? 0xFu : s.mode_mask == 2u ? 0x3u : 0xCu;
+    size_t off[9];
+    const size_t share_bytes = band_share_layout(d, n_shares, off);
+    for (int k = 0; k < n_shares; k++)
+        for (int i = 0; i < 8; i++) {
+            const int v = i >> 1, hv = view_rows(d, v), wv = view_cols(d, v);
+            if (!((vm >> v) & 1u)) continue;
+            const int r0 = share_row0(hv, k, n_shares), r1 = share_row0(hv, k + 1, n_shares);
+            int16_t *dst = ((i & 1) ? s.d_wtaR : s.d_wtaL) + (size_t)v * d.px + (size_t)r0 * wv;
+            if (r1 > r0) SCK(cudaMemcpyAsync(dst, shares_dev + (size_t)k * share_bytes + off[i], (size_t)(r1 - r0) * wv * sizeof(int16_t), cudaMemcpyDeviceToDevice, s.st));
+        }
+    return band_rest(ctx, s);
 }
 
 int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *state_in_dev, uint8_t *state_out_dev)

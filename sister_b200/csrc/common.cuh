@@ -58,6 +58,8 @@ void set_cell_order(Dims &d);
 
 __host__ __device__ inline int view_rows(const Dims &d, int v) { return v < 2 ? d.Hp : d.Wp; }
 __host__ __device__ inline int view_cols(const Dims &d, int v) { return v < 2 ? d.Wp : d.Hp; }
+// first row of share k when hv rows are dealt to n shares (share k = rows [share_row0(k), share_row0(k + 1)))
+__host__ __device__ inline int share_row0(int hv, int k, int n) { return (int)((long long)hv * k / n); }
 
 // image (i,j) -> view frame (r,c)
 __host__ __device__ inline void image_to_view(const Dims &d, int v, int i, int j, int &r, int &c)

@@ -45,8 +45,9 @@ void launch_census(const uint8_t *oriented, const Dims &d, unsigned long long *c
 
 // ---- match.cu ----
 // raw Hamming cost + WTA-left + WTA-right for the views in view_mask (census.cpp:54-146, postprocess.cpp:74-315)
+// share / n_shares: the rows [hv * share / n, hv * (share + 1) / n) of every view only (row bands; 0 / 1 = all rows)
 void launch_match_wta(const unsigned long long *census, const Dims &d, unsigned view_mask, int16_t *wtaL, int16_t *wtaR,
-                      cudaStream_t st, LaunchCounter &lc);
+                      cudaStream_t st, LaunchCounter &lc, int share = 0, int n_shares = 1);
 // in-place-semantics 3x3 median (postprocess.cpp:15-71 with src == dst), LRC (postprocess.cpp:318-341), masks (hpp:201-251)
 void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims &d, unsigned view_mask, int16_t *medL,
                             int16_t *medR, int16_t *lr_final, uint8_t *masks, int *status, cudaStream_t st, LaunchCounter &lc);

@@ -119,13 +119,15 @@ __device__ __forceinline__ void match_block(unsigned c1_s, unsigned c2_s, unsign
 
 // grid (max(hv), 4), block 32 * min(ceil(max(wv) / (32 K)), 13), dynamic smem: 2 * wv u64 + wv u32; three blocks per SM
 __global__ void __launch_bounds__(416, 3) k_match_wta(const unsigned long long *__restrict__ census, Dims d, unsigned view_mask,
-                                                    int16_t *__restrict__ wtaL, int16_t *__restrict__ wtaR)
+                                                    int16_t *__restrict__ wtaL, int16_t *__restrict__ wtaR, int share, int n_shares)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int v = blockIdx.y, r = blockIdx.x;
+    const int v = blockIdx.y;
     if (!((view_mask >> v) & 1u)) return;
     const int hv = view_rows(d, v), wv = view_cols(d, v);
-    if (r >= hv) return;
+    // (row bands: this launch matches the rows [hv * share / n, hv * (share + 1) / n) of every view)
+    const int r = blockIdx.x + share_row0(hv, share, n_shares);
+    if (r >= share_row0(hv, share + 1, n_shares)) return;
     int16_t *outL = wtaL + (size_t)v * d.px + (size_t)r * wv;
     int16_t *outR = wtaR + (size_t)v * d.px + (size_t)r * wv;
     const int tid = threadIdx.x;
@@ -158,15 +160,15 @@ __global__ void __launch_bounds__(416, 3) k_match_wta(const unsigned long long *
 }
 
 void launch_match_wta(const unsigned long long *census, const Dims &d, unsigned view_mask, int16_t *wtaL, int16_t *wtaR,
-                      cudaStream_t st, LaunchCounter &lc)
+                      cudaStream_t st, LaunchCounter &lc, int share, int n_shares)
 {
     int m = d.Wp > d.Hp ? d.Wp : d.Hp;
     size_t smem = (size_t)m * (8 + 8 + 4);
     lc.fail(optin_dynamic_smem((const void *)k_match_wta, smem));
     int warps = (m + 32 * kMatchK - 1) / (32 * kMatchK);
     if (warps > 13) warps = 13;
-    dim3 grid(m, 4);
-    k_match_wta<<<grid, 32 * warps, smem, st>>>(census, d, view_mask, wtaL, wtaR);
+    dim3 grid((m + n_shares - 1) / n_shares, 4);
+    k_match_wta<<<grid, 32 * warps, smem, st>>>(census, d, view_mask, wtaL, wtaR, share, n_shares);
     lc.add();
 }
 

@@ -14,16 +14,19 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("share_match", [True, False])
 @pytest.mark.parametrize("w,h,D,world,mode", [(96, 64, 32, 2, 0), (100, 76, 40, 3, 1), (52, 88, 136, 5, 2), (64, 48, 16, 7, 0), (72, 60, 264, 2, 0),
                                               (640, 480, 192, 4, 0)])
-def test_bands_on_one_gpu_equal_the_single_band_map(w, h, D, world, mode):
+def test_bands_on_one_gpu_equal_the_single_band_map(w, h, D, world, mode, share_match):
+    """share_match: every band matches 1/G of each view's rows and the packed maps are gathered (sister_band_submit_share /
+    _rest); otherwise every band matches the whole frame (sister_band_submit)."""
     import sister_b200
     from sister_b200.bands import EngineBandWorker, as_uint16, run_bands_in_process
 
     views = make_rig(w, h, D, seed=31 + world, channels=3 if w < 600 else 1)
     with sister_b200.Engine(w, h, D, n_slots=world) as eng:
         want = eng.compute(views, D, mode_mask=1 << mode)[mode]
-        workers = [EngineBandWorker(eng, views, D, r, world, mode=mode, slot=r) for r in range(world)]
+        workers = [EngineBandWorker(eng, views, D, r, world, mode=mode, slot=r, share_match=share_match) for r in range(world)]
         rows = run_bands_in_process(workers)
         got = np.concatenate([as_uint16(r) for r in rows], axis=0)
     assert got.shape == want.shape
