@@ -499,7 +499,8 @@ def run_bands(ctx: Dist, args, reps=2, check=True):
     """BASELINE.json configs[3]: ONE 4096x3072 D=384 frame by row bands over the ranks (sister_b200/bands.py): the column /
     diagonal state crosses the band borders exactly, over NCCL. Returns the dict for the line."""
     import sister_b200 as sb
-    from sister_b200.bands import EngineBandWorker, as_uint16, compute_banded, gather_band_rows, run_bands_in_process
+    from sister_b200.bands import (EngineBandWorker, as_uint16, compute_banded, connect_row_mailboxes, disconnect_row_mailboxes, gather_band_rows,
+                                   run_bands_in_process)
     torch = ctx.torch
     w, h, d = SHAPES["c4-bands"]
     views = make_rig(w, h, d, seed=1234, channels=1)
@@ -507,6 +508,9 @@ def run_bands(ctx: Dist, args, reps=2, check=True):
     times = []
     with sb.Engine(w, h, d, n_slots=1, device=ctx.local) as eng:
         worker = EngineBandWorker(eng, views, d, ctx.rank, ctx.world, mode=0)
+        streamed = False
+        if ctx.world > 1:
+            streamed = connect_row_mailboxes(worker, ctx.world, ctx.rank)  # the row sweeps of all bands run together, streamed over NVLink
         rows = None
         for rep in range(reps + 1):
             ctx.barrier()
@@ -526,6 +530,8 @@ def run_bands(ctx: Dist, args, reps=2, check=True):
             allt = [None] * ctx.world
             ctx.dist.all_gather_object(allt, mine)
             timeline = {f"rank{r}": t for r, t in enumerate(allt)}
+            if streamed:
+                disconnect_row_mailboxes(worker)
         equal, single_ms = None, None
         if check and ctx.rank == 0:
             eng.compute(views, d, mode_mask=1)
@@ -534,10 +540,10 @@ def run_bands(ctx: Dist, args, reps=2, check=True):
             single_ms = (time.perf_counter() - t0) * 1e3
             equal = bool((as_uint16(full) == want).all())
     ms = statistics.median(times)
-    return {"what": "one frame by row bands, exact state hand-over between the bands (NCCL send/recv)", "shape": [w, h, d], "n_gpus": ctx.world,
+    return {"what": "one frame by row bands, exact state hand-over between the bands (row sweeps: mailboxes in peer memory; column sweeps: NCCL send/recv)", "shape": [w, h, d], "n_gpus": ctx.world,
             "ms_per_frame": ms, "frames_per_s": 1e3 / ms, "gcost_evals_per_s": cost_evals(w, h, d) / ms / 1e6,
             "single_gpu_host_call_ms": single_ms, "equal_to_single_gpu": equal,
-            "wta_rows_shared": ctx.world > 1, "timeline_ms_end_of_phase": timeline}
+            "wta_rows_shared": ctx.world > 1, "row_sweeps_streamed": streamed, "timeline_ms_end_of_phase": timeline}
 
 
 def main():

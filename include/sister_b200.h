@@ -174,11 +174,35 @@ int sister_band_submit_share(sister_ctx *ctx, int slot, const uint8_t *const vie
                              uint8_t *share_out_dev);
 int sister_band_submit_rest(sister_ctx *ctx, int slot, const uint8_t *shares_dev, int n_shares);
 int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *state_in_dev, uint8_t *state_out_dev);
+/* The same aggregation with the ROW sweeps of all bands running at the same time. A row sweep takes as many steps as the
+ * frame is wide however few rows the band has, so handing its state over only when a band has finished (sister_band_vertical)
+ * serialises G sweeps of full length. Instead the band below reads the rider states from a mailbox in its own memory WHILE the
+ * band above writes them there, one step behind -- exactly the hand-over between two thread blocks of a sweep, across NVLink:
+ *   sister_band_rows     passes: 1 = pass 0, 2 = pass 1, 3 = both in one launch. in_pass0: this band's mailbox for pass 0
+ *                        (written by the band above), out_pass0: the mailbox of the band below (peer memory, sister_ipc_open);
+ *                        in_pass1 / out_pass1 likewise with below / above. A mailbox is sister_band_state_bytes() of zero-
+ *                        initialised device memory; NULL on the side where the band has no neighbour. tag: 1 .. 15, the same
+ *                        on all bands of a frame and different from the previous frame's (every word carries it, so a
+ *                        reader never takes a word of the frame before for one of this frame).
+ *   sister_band_columns  the column sweep of one pass alone, states as in sister_band_vertical (still handed over when the
+ *                        band has finished: a column sweep has only as many steps as the band has rows).
+ * The bands' sister_band_rows must all be enqueued before any of them is waited for; a band whose neighbour never starts
+ * reports SISTER_E_INTERNAL (status bit "spin timeout") after a few seconds instead of hanging. */
+int sister_band_rows(sister_ctx *ctx, int slot, int passes, const uint8_t *in_pass0, uint8_t *out_pass0, const uint8_t *in_pass1,
+                     uint8_t *out_pass1, unsigned tag);
+int sister_band_columns(sister_ctx *ctx, int slot, int pass, const uint8_t *state_in_dev, uint8_t *state_out_dev);
 int sister_band_finish(sister_ctx *ctx, int slot, uint16_t *out_dev);
 
 /* Plain device memory helpers so that a host language needs no CUDA binding of its own. */
 int sister_dev_alloc(sister_ctx *ctx, size_t bytes, void **dev_ptr);
 int sister_dev_free(sister_ctx *ctx, void *dev_ptr);
+int sister_dev_memset(sister_ctx *ctx, void *dev_ptr, int value, size_t bytes);
+/* Memory of sister_dev_alloc made visible to the other processes of the box (one process per GPU, row bands): the owner
+ * exports a 64-byte handle (cudaIpcMemHandle_t), a peer opens it into its own address space (peer access over NVLink) and
+ * closes it before the owner frees the memory. */
+int sister_ipc_export(sister_ctx *ctx, void *dev_ptr, unsigned char handle_out[64]);
+int sister_ipc_open(sister_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
+int sister_ipc_close(sister_ctx *ctx, void *dev_ptr);
 /* Page-locked host memory. sister_submit / sister_compute(_batch) copy a dense view that lives in page-locked memory
  * (from here, cudaHostAlloc or cudaHostRegister) to the device directly; other buffers are staged through the slot's
  * own pinned area with one extra memcpy. */

@@ -19,7 +19,8 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sister_b200  # noqa: E402
-from sister_b200.bands import EngineBandWorker, as_uint16, compute_banded, gather_band_rows  # noqa: E402
+from sister_b200.bands import (EngineBandWorker, as_uint16, compute_banded, connect_row_mailboxes, disconnect_row_mailboxes,  # noqa: E402
+                               gather_band_rows)
 from sister_b200.synth import make_rig  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -29,6 +30,7 @@ ap.add_argument("--disp", dest="d", type=int, default=384)
 ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--no-stream-rows", action="store_true", help="hand the row sweeps' states over when a band has finished (sister_band_vertical)")
 a = ap.parse_args()
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -40,6 +42,7 @@ hp = a.h + 2 * a.d
 times = []
 with sister_b200.Engine(a.w, a.h, a.d, n_slots=1, device=local) as eng:
     worker = EngineBandWorker(eng, views, a.d, rank, world, mode=a.mode)
+    streamed = world > 1 and not a.no_stream_rows and connect_row_mailboxes(worker, world, rank)
     for rep in range(a.reps + 1):
         if world > 1:
             dist.barrier()
@@ -64,8 +67,10 @@ with sister_b200.Engine(a.w, a.h, a.d, n_slots=1, device=local) as eng:
         single_ms = (time.perf_counter() - t0) * 1e3
         ok = bool((as_uint16(full) == want).all())
         print("bands == single GPU:", ok)
+    if getattr(worker, "stream_rows", False):
+        disconnect_row_mailboxes(worker)
     if rank == 0:
-        print(json.dumps({"what": "one frame by row bands", "shape": [a.w, a.h, a.d], "n_gpus": world, "band_ms": times,
+        print(json.dumps({"what": "one frame by row bands", "row_sweeps_streamed": bool(streamed), "shape": [a.w, a.h, a.d], "n_gpus": world, "band_ms": times,
                           "single_gpu_host_call_ms": single_ms, "equal": ok}))
 if world > 1:
     dist.destroy_process_group()

@@ -22,10 +22,10 @@ _i16p = C.POINTER(C.c_int16)
 # every symbol include/sister_b200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = (
     "sister_create", "sister_destroy", "sister_compute", "sister_compute_batch", "sister_submit", "sister_wait",
-    "sister_submit_device", "sister_sync", "sister_dev_alloc", "sister_dev_free", "sister_host_alloc", "sister_host_free", "sister_dev_upload",
+    "sister_submit_device", "sister_sync", "sister_dev_alloc", "sister_dev_free", "sister_dev_memset", "sister_ipc_export", "sister_ipc_open", "sister_ipc_close", "sister_host_alloc", "sister_host_free", "sister_dev_upload",
     "sister_dev_download", "sister_set_profiling", "sister_region_begin", "sister_region_end", "sister_get_stage_ms", "sister_get_stage_launches",
     "sister_get_launch_count", "sister_debug_fetch", "sister_set_test_taps", "sister_set_full_frame",
-    "sister_stereo", "sister_create_band", "sister_band_state_bytes", "sister_band_submit", "sister_band_share_bytes", "sister_band_submit_share", "sister_band_submit_rest", "sister_band_vertical", "sister_band_finish", "sister_test_sgm", "sister_strerror", "sister_last_error",
+    "sister_stereo", "sister_create_band", "sister_band_state_bytes", "sister_band_submit", "sister_band_share_bytes", "sister_band_submit_share", "sister_band_submit_rest", "sister_band_rows", "sister_band_columns", "sister_band_vertical", "sister_band_finish", "sister_test_sgm", "sister_strerror", "sister_last_error",
     "sister_version",
 )
 
@@ -83,6 +83,14 @@ def load_library():
     L.sister_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.sister_dev_free.restype = C.c_int
     L.sister_dev_free.argtypes = [vp, vp]
+    L.sister_dev_memset.restype = C.c_int
+    L.sister_dev_memset.argtypes = [vp, vp, C.c_int, C.c_size_t]
+    L.sister_ipc_export.restype = C.c_int
+    L.sister_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    L.sister_ipc_open.restype = C.c_int
+    L.sister_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.sister_ipc_close.restype = C.c_int
+    L.sister_ipc_close.argtypes = [vp, vp]
     L.sister_host_alloc.restype = C.c_int
     L.sister_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.sister_host_free.restype = C.c_int
@@ -121,6 +129,10 @@ def load_library():
                                            C.c_int, C.c_int, vp]
     L.sister_band_submit_rest.restype = C.c_int
     L.sister_band_submit_rest.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.sister_band_rows.restype = C.c_int
+    L.sister_band_rows.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_uint]
+    L.sister_band_columns.restype = C.c_int
+    L.sister_band_columns.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.sister_band_vertical.restype = C.c_int
     L.sister_band_vertical.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.sister_band_finish.restype = C.c_int
@@ -245,6 +257,23 @@ class Engine:
         self._chk(self.lib.sister_wait(self.ctx, slot, oarr, None))
         return outs
 
+    # -- memory shared with the other processes of the box (row bands)
+    def dev_memset(self, ptr: int, value: int, nbytes: int):
+        self._chk(self.lib.sister_dev_memset(self.ctx, C.c_void_p(ptr), value, nbytes))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._chk(self.lib.sister_ipc_export(self.ctx, C.c_void_p(ptr), buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._chk(self.lib.sister_ipc_open(self.ctx, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr: int):
+        self._chk(self.lib.sister_ipc_close(self.ctx, C.c_void_p(ptr)))
+
     # -- device-resident path (bench `value`)
     def dev_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
@@ -324,6 +353,15 @@ class Engine:
 
     def band_submit_rest(self, slot: int, shares_ptr: int, n_shares: int):
         self._chk(self.lib.sister_band_submit_rest(self.ctx, slot, C.c_void_p(shares_ptr), n_shares))
+
+    def band_rows(self, slot: int, passes: int, in0: int, out0: int, in1: int, out1: int, tag: int):
+        """Row sweeps of the band with their rider states streamed to / from the neighbouring bands' mailboxes (0 = none)."""
+        p = lambda x: C.c_void_p(x) if x else None  # noqa: E731
+        self._chk(self.lib.sister_band_rows(self.ctx, slot, passes, p(in0), p(out0), p(in1), p(out1), tag))
+
+    def band_columns(self, slot: int, pass_: int, state_in_ptr: int, state_out_ptr: int):
+        self._chk(self.lib.sister_band_columns(self.ctx, slot, pass_, C.c_void_p(state_in_ptr) if state_in_ptr else None,
+                                               C.c_void_p(state_out_ptr) if state_out_ptr else None))
 
     def band_vertical(self, slot: int, pass_: int, state_in_ptr: int, state_out_ptr: int):
         self._chk(self.lib.sister_band_vertical(self.ctx, slot, pass_, C.c_void_p(state_in_ptr) if state_in_ptr else None,

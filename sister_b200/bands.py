@@ -127,6 +127,13 @@ def compute_banded(worker, world: int, rank: int, group=None, trace=None):
     else:
         worker.submit()
         mark("stage+census+match+masks+fuse band")
+    # the row sweeps of all bands run at the same time, their states streamed through mailboxes in the neighbour's memory
+    # (worker.stream_rows: the mailboxes were connected by connect_row_mailboxes); then only the column sweeps are left
+    # for the two wavefronts
+    streamed = world > 1 and getattr(worker, "stream_rows", False)
+    if streamed:
+        worker.rows()
+        mark("row sweeps (streamed between the bands)")
     inbox = {}
     outbox = {}
     for kind, p, peer in band_program(world, rank):
@@ -138,8 +145,9 @@ def compute_banded(worker, world: int, rank: int, group=None, trace=None):
         elif kind == "compute":
             src = rank - 1 if p == 0 else rank + 1
             dst = rank + 1 if p == 0 else rank - 1
-            outbox[p] = worker.vertical(p, inbox.get(p) if 0 <= src < world else None, 0 <= dst < world)
-            mark(f"sweeps pass {p}")
+            step = worker.columns if streamed else worker.vertical
+            outbox[p] = step(p, inbox.get(p) if 0 <= src < world else None, 0 <= dst < world)
+            mark(f"{'column sweep' if streamed else 'sweeps'} pass {p}")
         else:
             dist.send(outbox[p], dst=peer, group=group)
             mark(f"send state pass {p}")
@@ -162,6 +170,14 @@ def run_bands_in_process(workers):
     else:
         for w in workers:
             w.submit()
+    streamed = world > 1 and all(getattr(w, "stream_rows", False) for w in workers)
+    if streamed:
+        # one GPU runs all the bands: a kernel whose producer is queued BEHIND it would wait for nothing, so the producers
+        # go first -- pass 0 top to bottom, then pass 1 bottom to top (on G GPUs every band has its own and one launch does both)
+        for w in workers:
+            w.rows(passes=1)
+        for w in reversed(workers):
+            w.rows(passes=2)
     progs = [band_program(world, r) for r in range(world)]
     pc = [0] * world
     inbox = [dict() for _ in range(world)]
@@ -175,7 +191,8 @@ def run_bands_in_process(workers):
             if kind == "compute":
                 src = r - 1 if p == 0 else r + 1
                 dst = r + 1 if p == 0 else r - 1
-                outbox[r][p] = workers[r].vertical(p, inbox[r].get(p) if 0 <= src < world else None, 0 <= dst < world)
+                step = workers[r].columns if streamed else workers[r].vertical
+                outbox[r][p] = step(p, inbox[r].get(p) if 0 <= src < world else None, 0 <= dst < world)
             elif kind == "send":
                 if not (pc[peer] < len(progs[peer]) and progs[peer][pc[peer]] == ("recv", p, r)):
                     continue
@@ -260,6 +277,33 @@ class EngineBandWorker:
         self.torch.cuda.current_stream().synchronize()  # the gathered shares were written on torch's stream
         self.eng.band_submit_rest(self.slot, gathered.data_ptr(), n_shares)
 
+    # ---- row sweeps streamed between the bands
+    def make_row_mailboxes(self):
+        """This band's two mailboxes (pass 0: written by the band above, pass 1: by the band below), zero-filled device memory
+        from the library's allocator (so that it can be exported to the neighbours' processes)."""
+        self.mbox = [self.eng.dev_alloc(self.state_bytes) for _ in range(2)]
+        for m in self.mbox:
+            self.eng.dev_memset(m, 0, self.state_bytes)
+        self.peer_out = [0, 0]   # pass 0: the mailbox of the band below, pass 1: of the band above
+        self.stream_rows = True
+        self.frame = 0
+        return self.mbox
+
+    def rows(self, passes: int = 3):
+        if passes != 2:            # a new frame starts with pass 0 (or with the launch that does both)
+            self.frame += 1
+        tag = (self.frame - 1) % 15 + 1
+        self.eng.band_rows(self.slot, passes, self.mbox[0], self.peer_out[0], self.mbox[1], self.peer_out[1], tag)
+
+    def columns(self, p: int, state_in, want_out: bool):
+        out = self.new_state() if want_out else None
+        if state_in is not None:
+            self.torch.cuda.current_stream().synchronize()
+        self.eng.band_columns(self.slot, p, state_in.data_ptr() if state_in is not None else 0, out.data_ptr() if want_out else 0)
+        if want_out:
+            self.eng.sync(self.slot)
+        return out
+
     def vertical(self, p: int, state_in, want_out: bool):
         out = self.new_state() if want_out else None
         if state_in is not None:
@@ -278,6 +322,59 @@ class EngineBandWorker:
         self.eng.sync(self.slot)
         a, b = crop_rows_of_band(self.D, self.h, self.row0, self.row1)
         return self.out[a:b]
+
+
+def connect_row_mailboxes(worker, world: int, rank: int, group=None):
+    """One process per GPU: every worker makes its two mailboxes, the 64-byte IPC handles go round (all_gather_object), and each
+    worker opens the neighbours' -- pass 0 writes into the band below's, pass 1 into the band above's (peer access over NVLink).
+    Returns whether the mailboxes are connected (the same answer on every rank)."""
+    import torch.distributed as dist
+
+    mbox = worker.make_row_mailboxes()
+    handles = [None] * world
+    dist.all_gather_object(handles, [worker.eng.ipc_export(m) for m in mbox], group=group)
+    ok = True
+    try:
+        if rank + 1 < world:
+            worker.peer_out[0] = worker.eng.ipc_open(handles[rank + 1][0])
+        if rank > 0:
+            worker.peer_out[1] = worker.eng.ipc_open(handles[rank - 1][1])
+    except Exception:  # no peer access between two of the GPUs: every rank falls back to the hand-over at the end of a band
+        ok = False
+    oks = [None] * world
+    dist.all_gather_object(oks, ok, group=group)
+    if not all(oks):
+        disconnect_row_mailboxes(worker, group=group)
+        return False
+    return True
+
+
+def disconnect_row_mailboxes(worker, group=None):
+    """Close the neighbours' mailboxes, then (after everybody has) free this worker's own."""
+    import torch.distributed as dist
+
+    worker.eng.sync(worker.slot)
+    for p in worker.peer_out:
+        if p:
+            worker.eng.ipc_close(p)
+    worker.peer_out = [0, 0]
+    worker.stream_rows = False
+    if dist.is_initialized():
+        dist.barrier(group=group)
+    for m in worker.mbox:
+        worker.eng.dev_free(m)
+    worker.mbox = []
+
+
+def connect_row_mailboxes_in_process(workers):
+    """All bands in one process (one GPU): the neighbours' mailboxes are plain pointers."""
+    for w in workers:
+        w.make_row_mailboxes()
+    for r, w in enumerate(workers):
+        if r + 1 < len(workers):
+            w.peer_out[0] = workers[r + 1].mbox[0]
+        if r > 0:
+            w.peer_out[1] = workers[r - 1].mbox[1]
 
 
 def as_uint16(t) -> np.ndarray:

@@ -603,6 +603,50 @@ int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *sta
     return SISTER_OK;
 }
 
+int sister_band_rows(sister_ctx *ctx, int slot, int passes, const uint8_t *in_pass0, uint8_t *out_pass0, const uint8_t *in_pass1, uint8_t *out_pass1,
+                     unsigned tag)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    Slot &s = ctx->slots[slot];
+    if (passes < 1 || passes > 3 || s.band_r1 <= s.band_r0) { ctx->err = "sister_band_submit first; passes is 1 (pass 0), 2 (pass 1) or 3 (both)"; return SISTER_E_ARG; }
+    if (tag < 1 || tag > 15) { ctx->err = "the frame tag must be 1 .. 15 and differ from the previous frame's"; return SISTER_E_ARG; }
+    const bool top = s.band_r0 == 0, bottom = s.band_r1 == s.dims.Hp;
+    // pass 0 flows down (in from the band above, out to the band below), pass 1 up; a missing mailbox would silently restart
+    // or drop the diagonal paths at the band border
+    if (((passes & 1) && ((!top && !in_pass0) || (!bottom && !out_pass0))) || ((passes & 2) && ((!bottom && !in_pass1) || (!top && !out_pass1)))) {
+        ctx->err = "a mailbox is NULL although the band has a neighbour on that side";
+        return SISTER_E_ARG;
+    }
+    SCK(cudaSetDevice(ctx->device));
+    BandStream bs;
+    bs.in[0] = top ? nullptr : in_pass0;     bs.out[0] = bottom ? nullptr : out_pass0;
+    bs.in[2] = bottom ? nullptr : in_pass1;  bs.out[2] = top ? nullptr : out_pass1;
+    bs.tag = tag;
+    launch_sgm_band_rows(s.d_fused - s.sgm.row_shift, s.dims, s.band_r0, s.band_r1, ((passes & 1) ? 1u : 0u) | ((passes & 2) ? 4u : 0u), bs, s.sgm,
+                         s.d_status, s.st, ctx->lc);
+    SCK(cudaGetLastError());
+    SCK(take_launch_error(ctx));
+    return SISTER_OK;
+}
+
+int sister_band_columns(sister_ctx *ctx, int slot, int pass, const uint8_t *state_in_dev, uint8_t *state_out_dev)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    Slot &s = ctx->slots[slot];
+    if (pass < 0 || pass > 1 || s.band_r1 <= s.band_r0) { ctx->err = "sister_band_submit first; pass is 0 or 1"; return SISTER_E_ARG; }
+    SCK(cudaSetDevice(ctx->device));
+    const bool first_of_pass = pass == 0 ? s.band_r0 == 0 : s.band_r1 == s.dims.Hp;
+    const bool last_of_pass = pass == 0 ? s.band_r1 == s.dims.Hp : s.band_r0 == 0;
+    if (!first_of_pass && !state_in_dev) { ctx->err = "state_in_dev is NULL but the band is not the first of this pass"; return SISTER_E_ARG; }
+    if (!last_of_pass && !state_out_dev) { ctx->err = "state_out_dev is NULL but the band is not the last of this pass"; return SISTER_E_ARG; }
+    launch_sgm_band(5 + pass, s.d_fused - s.sgm.row_shift, s.dims, s.band_r0, s.band_r1, state_in_dev, state_out_dev, s.sgm, nullptr, nullptr, s.d_status, s.st, ctx->lc);
+    SCK(cudaGetLastError());
+    SCK(take_launch_error(ctx));
+    return SISTER_OK;
+}
+
 int sister_band_finish(sister_ctx *ctx, int slot, uint16_t *out_dev)
 {
     int rc = slot_ok(ctx, slot);
@@ -643,6 +687,40 @@ int sister_dev_free(sister_ctx *ctx, void *dev_ptr)
     if (!ctx) return SISTER_E_ARG;
     SCK(cudaSetDevice(ctx->device));
     SCK(cudaFree(dev_ptr));
+    return SISTER_OK;
+}
+// ---- device memory shared between the processes of one box (one process per GPU): the band mailboxes of the row sweeps
+int sister_ipc_export(sister_ctx *ctx, void *dev_ptr, unsigned char handle_out[64])
+{
+    if (!ctx || !dev_ptr || !handle_out) return SISTER_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C ABI passes the handle as 64 bytes");
+    SCK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    SCK(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle_out, &h, 64);
+    return SISTER_OK;
+}
+int sister_ipc_open(sister_ctx *ctx, const unsigned char handle[64], void **dev_ptr)
+{
+    if (!ctx || !handle || !dev_ptr) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    SCK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SISTER_OK;
+}
+int sister_ipc_close(sister_ctx *ctx, void *dev_ptr)
+{
+    if (!ctx || !dev_ptr) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    SCK(cudaIpcCloseMemHandle(dev_ptr));
+    return SISTER_OK;
+}
+int sister_dev_memset(sister_ctx *ctx, void *dev_ptr, int value, size_t bytes)
+{
+    if (!ctx || !dev_ptr) return SISTER_E_ARG;
+    SCK(cudaSetDevice(ctx->device));
+    SCK(cudaMemset(dev_ptr, value, bytes));
     return SISTER_OK;
 }
 int sister_host_alloc(sister_ctx *ctx, size_t bytes, void **host_ptr)

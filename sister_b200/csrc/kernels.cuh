@@ -90,6 +90,15 @@ void launch_wta_right_sum(const uint16_t *sum, const Dims &d, int16_t *outR, cud
 // neighbouring band's state_out; null on the first band of the pass) and leaving their state in state_out (null on the
 // last), 3 = final sum / WTA / encode of the band's rows. State: sgm_band_state_bytes.
 size_t sgm_band_state_bytes(const Dims &d);
+// row sweeps streamed between the bands: per sweep (0: pass 0, 2: pass 1) this band's mailbox and the neighbour's, and the
+// tag (1..15) every word of this frame carries; see launch_sgm_band_rows in sgm.cu
+struct BandStream {
+    const uint8_t *in[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t *out[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned tag = 0;
+};
+void launch_sgm_band_rows(const uint8_t *fused, const Dims &d, int band_r0, int band_r1, unsigned mask, const BandStream &bs, SgmScratch &sc,
+                          int *status, cudaStream_t st, LaunchCounter &lc);
 void launch_sgm_band(int what, const uint8_t *fused, const Dims &d, int band_r0, int band_r1, const uint8_t *state_in, uint8_t *state_out,
                      SgmScratch &sc, int16_t *raw_disp, uint16_t *out, int *status, cudaStream_t st, LaunchCounter &lc);
 

@@ -78,6 +78,9 @@ struct SweepGeo {
     // row bands: row sweeps read / leave one rider state per step, column sweeps [carrier states | rider states] per chain
     const uint8_t *band_in;
     uint8_t *band_out;
+    // != 0: the row sweep's band entries are a mailbox between two GPUs that run at the same time -- every word carries this
+    // tag (like the block mailbox), the reader polls for it, and both sides use system-scope accesses (peer memory)
+    unsigned band_tag;
 };
 struct SweepPlan {
     SweepGeo g[4];
@@ -112,6 +115,9 @@ __device__ __forceinline__ uint4 lds128v(unsigned a) { uint4 v; asm volatile("ld
 __device__ __forceinline__ void sts64(unsigned a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};\n" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 __device__ __forceinline__ uint32_t ld_relaxed(const uint8_t *p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_relaxed(uint8_t *p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
+// the same towards / from another GPU's memory (row sweeps streamed between row bands)
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint8_t *p) { uint32_t v; asm volatile("ld.relaxed.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_relaxed_sys(uint8_t *p, uint32_t v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 // The step barrier of a block (compute warps + mailbox warp; warps without a role have left). Warps of different roles reach
 // it from different places of the code, which bar.sync permits (every warp executes it as a whole) but compute-sanitizer's
 // synccheck reports as "divergent threads in block"; -DSISTER_ONE_BARRIER_INSTRUCTION routes every role through one
@@ -369,11 +375,15 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
     const uint8_t *src = nullptr;
     unsigned src_tag = 0u, src_mask = 0u;
     if (b > 0) { src = mailbox + (g.mb_off + (long long)(b - 1) * T) * EB; src_tag = tagword; src_mask = 0x80808080u; }
-    else if (g.row && g.band_in) src = g.band_in; // the band before left one state per step, untagged
+    else if (g.row && g.band_in) { // the band before leaves one state per step: all of them already there (untagged), or
+        src = g.band_in;           // arriving while this band runs (tagged, written by the neighbouring GPU)
+        if (g.band_tag) { src_tag = g.band_tag; src_mask = 0x80808080u; }
+    }
     uint8_t *dst = nullptr;
     unsigned dst_tag = 0u;
     if (b < g.nblk - 1) { dst = mailbox + (g.mb_off + (long long)b * T) * EB; dst_tag = tagword; }
-    else if (g.row && g.band_out) dst = g.band_out;
+    else if (g.row && g.band_out) { dst = g.band_out; dst_tag = g.band_tag; }
+    const bool src_sys = b == 0 && g.band_tag != 0u, dst_sys = b == g.nblk - 1 && g.band_tag != 0u;
     const long long lane_off = (long long)li.sl * 4;
     uint32_t a[NR];
     // entry 0 at the first step. A column sweep continued from the band before takes the predecessor of the block's first
@@ -396,7 +406,7 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
         if (imp && src && s < T - 1) {
             const uint8_t *e = src + (long long)s * EB + lane_off;
 #pragma unroll
-            for (int k = 0; k < NH; k++) w[k] = ld_relaxed(e + (long long)k * LPC * 4);
+            for (int k = 0; k < NH; k++) w[k] = src_sys ? ld_relaxed_sys(e + (long long)k * LPC * 4) : ld_relaxed(e + (long long)k * LPC * 4);
         } else {
 #pragma unroll
             for (int k = 0; k < NH; k++) w[k] = src_tag;
@@ -417,7 +427,10 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
             state_to_words<NR>(a, dst_tag, w);
             uint8_t *e = dst + (long long)(s - 1) * EB + lane_off;
 #pragma unroll
-            for (int k = 0; k < NH; k++) st_relaxed(e + (long long)k * LPC * 4, w[k]);
+            for (int k = 0; k < NH; k++) {
+                if (dst_sys) st_relaxed_sys(e + (long long)k * LPC * 4, w[k]);
+                else st_relaxed(e + (long long)k * LPC * 4, w[k]);
+            }
         }
         // ---- deliver the predecessor's state after step s for step s + 1 (read two entries ahead)
         uint32_t w[NH];
@@ -442,7 +455,7 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
                 if (imp) {
                     const uint8_t *e = src + (long long)s * EB + lane_off;
 #pragma unroll
-                    for (int k = 0; k < NH; k++) w[k] = ld_relaxed(e + (long long)k * LPC * 4);
+                    for (int k = 0; k < NH; k++) w[k] = src_sys ? ld_relaxed_sys(e + (long long)k * LPC * 4) : ld_relaxed(e + (long long)k * LPC * 4);
                 }
             }
             if (imp) {
@@ -458,7 +471,10 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
         state_to_words<NR>(a, dst_tag, w);
         uint8_t *e = dst + (long long)(T - 1) * EB + lane_off;
 #pragma unroll
-        for (int k = 0; k < NH; k++) st_relaxed(e + (long long)k * LPC * 4, w[k]);
+        for (int k = 0; k < NH; k++) {
+            if (dst_sys) st_relaxed_sys(e + (long long)k * LPC * 4, w[k]);
+            else st_relaxed(e + (long long)k * LPC * 4, w[k]);
+        }
     }
 }
 
@@ -731,7 +747,7 @@ size_t sgm_mailbox_bytes(int max_w, int max_h, int max_d, int band_rows)
 size_t sgm_band_state_bytes(const Dims &d) { return (size_t)(3LL * d.Wp * entry_bytes(d)); }
 
 template <int NR, int LPC, bool FULL, bool IL>
-static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi, int b0, int b1, unsigned mask, const uint8_t *band_in, uint8_t *band_out,
+static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi, int b0, int b1, unsigned mask, const uint8_t *band_in, uint8_t *band_out, const BandStream *bs,
                             SgmScratch &sc, int *status, cudaStream_t st, LaunchCounter &lc)
 {
     constexpr int CPW = 32 / LPC;
@@ -795,6 +811,13 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
         const bool first = g.row ? g.n0 == 0 : g.t0 == 0; // starts at the pass's first line: nothing to continue
         g.band_in = (band_in && !first) ? band_in + off : nullptr;
         g.band_out = band_out ? band_out + off : nullptr;
+        g.band_tag = 0u;
+        if (bs && g.row) { // row sweeps streamed between the GPUs of two neighbouring bands: one mailbox per sweep and direction
+            g.band_in = first ? nullptr : bs->in[s];
+            g.band_out = bs->out[s];
+            const unsigned e = bs->tag & 15u;
+            g.band_tag = ((e & 1u) << 7) | (((e >> 1) & 1u) << 15) | (((e >> 2) & 1u) << 23) | (((e >> 3) & 1u) << 31);
+        }
     }
     // epoch tags: every entry a launch reads is written by that launch, so the tag only has to differ from the previous
     // launch of the same geometry; anything else clears the mailbox first
@@ -815,7 +838,7 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
 }
 
 template <int LPC, int NRMAX>
-static void launch_sweeps_lpc(const uint8_t *fused, const Dims &d, const Roi &roi, int b0, int b1, unsigned mask, const uint8_t *band_in, uint8_t *band_out,
+static void launch_sweeps_lpc(const uint8_t *fused, const Dims &d, const Roi &roi, int b0, int b1, unsigned mask, const uint8_t *band_in, uint8_t *band_out, const BandStream *bs,
                               SgmScratch &sc, int *status, cudaStream_t st, LaunchCounter &lc)
 {
     const int nr = d.nr;
@@ -824,10 +847,10 @@ static void launch_sweeps_lpc(const uint8_t *fused, const Dims &d, const Roi &ro
     case N:                                                                                                                    \
         if constexpr (N <= NRMAX) {                                                                                            \
             if constexpr (N % 4 == 2) {                                                                                        \
-                if (d.interleaved) { launch_sweeps_t<N, LPC, true, true>(fused, d, roi, b0, b1, mask, band_in, band_out, sc, status, st, lc); break; } \
+                if (d.interleaved) { launch_sweeps_t<N, LPC, true, true>(fused, d, roi, b0, b1, mask, band_in, band_out, bs, sc, status, st, lc); break; } \
             }                                                                                                                  \
-            if (full) launch_sweeps_t<N, LPC, true, false>(fused, d, roi, b0, b1, mask, band_in, band_out, sc, status, st, lc);  \
-            else launch_sweeps_t<N, LPC, false, false>(fused, d, roi, b0, b1, mask, band_in, band_out, sc, status, st, lc);      \
+            if (full) launch_sweeps_t<N, LPC, true, false>(fused, d, roi, b0, b1, mask, band_in, band_out, bs, sc, status, st, lc);  \
+            else launch_sweeps_t<N, LPC, false, false>(fused, d, roi, b0, b1, mask, band_in, band_out, bs, sc, status, st, lc);      \
         }                                                                                                                      \
         break;
     switch (nr) {
@@ -837,14 +860,14 @@ static void launch_sweeps_lpc(const uint8_t *fused, const Dims &d, const Roi &ro
 #undef SISTER_SWEEPS_CASE
 }
 
-static void launch_sweeps(const uint8_t *fused, const Dims &d, const Roi &roi, int b0, int b1, unsigned mask, const uint8_t *band_in, uint8_t *band_out,
+static void launch_sweeps(const uint8_t *fused, const Dims &d, const Roi &roi, int b0, int b1, unsigned mask, const uint8_t *band_in, uint8_t *band_out, const BandStream *bs,
                           SgmScratch &sc, int *status, cudaStream_t st, LaunchCounter &lc)
 {
 #ifdef SISTER_DEBUG_HOOKS
     if (const char *e = getenv("SISTER_DEBUG_SWEEP_MASK")) mask &= (unsigned)atoi(e); // measurement aid: run some of the sweeps only
 #endif
-    if (d.lpc == 8) launch_sweeps_lpc<8, 12>(fused, d, roi, b0, b1, mask, band_in, band_out, sc, status, st, lc); // four chains per warp
-    else launch_sweeps_lpc<16, 16>(fused, d, roi, b0, b1, mask, band_in, band_out, sc, status, st, lc);           // two (D <= 512, check_shape)
+    if (d.lpc == 8) launch_sweeps_lpc<8, 12>(fused, d, roi, b0, b1, mask, band_in, band_out, bs, sc, status, st, lc); // four chains per warp
+    else launch_sweeps_lpc<16, 16>(fused, d, roi, b0, b1, mask, band_in, band_out, bs, sc, status, st, lc);           // two (D <= 512, check_shape)
 }
 
 static void launch_final(const uint8_t *fused, const uint8_t *vols, size_t vol_stride, const Dims &d, const Roi &roi, uint16_t *sum, int16_t *raw_disp,
@@ -862,14 +885,15 @@ void launch_sgm(const uint8_t *fused, const Dims &d, bool full_frame, SgmScratch
                 int *status, cudaStream_t st, LaunchCounter &lc)
 {
     const Roi roi = make_roi(d, full_frame);
-    launch_sweeps(fused, d, roi, 0, d.Hp, 0xFu, nullptr, nullptr, sc, status, st, lc);
+    launch_sweeps(fused, d, roi, 0, d.Hp, 0xFu, nullptr, nullptr, nullptr, sc, status, st, lc);
     launch_final(fused, sc.vols - sc.row_shift, sc.vol_stride ? sc.vol_stride : (size_t)d.cells, d, roi, sum, raw_disp, out, st);
     lc.add();
 }
 
 // ---- row bands (one band per GPU; crop-only aggregation). what: 1 = the two sweeps of pass 0 inside the band (state_in from
 // the band above, state_out for the band below), 2 = those of pass 1 (state_in from the band below, state_out for the band
-// above), 3 = final sum / WTA / encode of the band's rows of the crop.
+// above), 3 = final sum / WTA / encode of the band's rows of the crop; 5 / 6 = the column sweep of pass 0 / 1 alone (same
+// state layout; the row sweep's part of it is not touched).
 void launch_sgm_band(int what, const uint8_t *fused, const Dims &d, int band_r0, int band_r1, const uint8_t *state_in, uint8_t *state_out,
                      SgmScratch &sc, int16_t *raw_disp, uint16_t *out, int *status, cudaStream_t st, LaunchCounter &lc)
 {
@@ -880,8 +904,21 @@ void launch_sgm_band(int what, const uint8_t *fused, const Dims &d, int band_r0,
         launch_final(fused, sc.vols - sc.row_shift, sc.vol_stride ? sc.vol_stride : (size_t)d.cells, d, roi, nullptr, raw_disp, out, st);
         lc.add();
     } else {
-        launch_sweeps(fused, d, roi, band_r0, band_r1, what == 1 ? 0x3u : 0xCu, state_in, state_out, sc, status, st, lc);
+        const unsigned mask = what == 1 ? 0x3u : what == 2 ? 0xCu : what == 5 ? 0x2u : 0x8u;
+        launch_sweeps(fused, d, roi, band_r0, band_r1, mask, state_in, state_out, nullptr, sc, status, st, lc);
     }
+}
+
+// The row sweeps of the band (mask: 1 = pass 0, 4 = pass 1, 5 = both in one launch) with their rider states STREAMED between
+// the bands: bs.in[s] is this band's mailbox for sweep s (one entry per step, written by the neighbouring band's GPU while
+// this kernel runs, NULL on the first band of that direction), bs.out[s] the neighbour's mailbox this band writes into
+// (NULL on the last band). All bands run at the same time, one step behind each other -- the hand-over between two blocks
+// of a sweep, over NVLink.
+void launch_sgm_band_rows(const uint8_t *fused, const Dims &d, int band_r0, int band_r1, unsigned mask, const BandStream &bs, SgmScratch &sc,
+                          int *status, cudaStream_t st, LaunchCounter &lc)
+{
+    const Roi roi = make_roi(d, false);
+    launch_sweeps(fused, d, roi, band_r0, band_r1, mask & 0x5u, nullptr, nullptr, &bs, sc, status, st, lc);
 }
 
 } // namespace sister

@@ -33,6 +33,31 @@ def test_bands_on_one_gpu_equal_the_single_band_map(w, h, D, world, mode, share_
     assert (got == want).all(), f"{(got != want).sum()} pixels differ"
 
 
+@pytest.mark.parametrize("w,h,D,world", [(96, 64, 32, 2), (96, 64, 32, 5), (64, 48, 16, 7), (52, 88, 136, 3), (640, 480, 192, 4)])
+def test_row_sweeps_streamed_between_the_bands(w, h, D, world):
+    """sister_band_rows / sister_band_columns: the row sweeps of all bands run at the same time, each reading the rider states
+    from a mailbox the band before writes while it runs (tagged words, as between two blocks of a sweep); two frames in a row
+    (the tag changes), all three modes of one shape."""
+    import sister_b200
+    from sister_b200.bands import EngineBandWorker, as_uint16, connect_row_mailboxes_in_process, run_bands_in_process
+
+    views = make_rig(w, h, D, seed=91 + world, channels=1)
+    views2 = make_rig(w, h, D, seed=92 + world, channels=1, kind="plane")
+    with sister_b200.Engine(w, h, D, n_slots=world) as eng:
+        for mode in ((0, 1, 2) if w < 100 else (0,)):
+            for vv in (views, views2):
+                want = eng.compute(vv, D, mode_mask=1 << mode)[mode]
+                workers = [EngineBandWorker(eng, vv, D, r, world, mode=mode, slot=r) for r in range(world)]
+                connect_row_mailboxes_in_process(workers)
+                for frame in range(2):
+                    rows = run_bands_in_process(workers)
+                    got = np.concatenate([as_uint16(r) for r in rows], axis=0)
+                    assert (got == want).all(), f"mode {mode}, frame {frame}: {(got != want).sum()} pixels differ"
+                for wk in workers:
+                    for m in wk.mbox:
+                        eng.dev_free(m)
+
+
 @pytest.mark.parametrize("w,h,D,world", [(96, 64, 32, 3), (128, 96, 64, 4), (52, 88, 136, 2)])
 def test_band_contexts_hold_a_band_of_the_volumes_only(w, h, D, world):
     """sister_create_band: the fused and pair volumes of a slot hold max_band_rows rows of the padded frame; G such slots
