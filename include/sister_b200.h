@@ -185,12 +185,16 @@ int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *sta
  *                        on all bands of a frame and different from the previous frame's (every word carries it, so a
  *                        reader never takes a word of the frame before for one of this frame).
  *   sister_band_columns  the column sweep of one pass alone, states as in sister_band_vertical (still handed over when the
- *                        band has finished: a column sweep has only as many steps as the band has rows).
+ *                        band has finished: a column sweep has only as many steps as the band has rows). It runs on a second
+ *                        stream of the slot, beside the row sweeps; sister_band_columns_wait() blocks until the column sweeps
+ *                        enqueued so far are done (state_out_dev complete) without waiting for the row sweeps, and
+ *                        sister_band_finish orders the final sweep behind both.
  * The bands' sister_band_rows must all be enqueued before any of them is waited for; a band whose neighbour never starts
  * reports SISTER_E_INTERNAL (status bit "spin timeout") after a few seconds instead of hanging. */
 int sister_band_rows(sister_ctx *ctx, int slot, int passes, const uint8_t *in_pass0, uint8_t *out_pass0, const uint8_t *in_pass1,
                      uint8_t *out_pass1, unsigned tag);
 int sister_band_columns(sister_ctx *ctx, int slot, int pass, const uint8_t *state_in_dev, uint8_t *state_out_dev);
+int sister_band_columns_wait(sister_ctx *ctx, int slot);
 int sister_band_finish(sister_ctx *ctx, int slot, uint16_t *out_dev);
 
 /* Plain device memory helpers so that a host language needs no CUDA binding of its own. */

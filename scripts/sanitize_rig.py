@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One small rig through every kernel of the path -- the 5-view call (3 modes, crop-only and whole frame), the batch
-pipeline, the two-view path, an SGM stage call, a 3-band run on one GPU and a second, wider rig (the chunked median kernel) --
+pipeline, the two-view path, an SGM stage call, a 3-band run on one GPU (states handed over at the end of a band, then streamed) and a second, wider rig (the chunked median kernel) --
 for compute-sanitizer
 (scripts/sanitize.sh runs it under memcheck, racecheck, initcheck and synccheck)."""
 import os
@@ -31,6 +31,13 @@ with sister_b200.Engine(w, h, D, n_slots=3) as eng:
         rows = run_bands_in_process(workers)
         got = np.concatenate([as_uint16(r) for r in rows], axis=0)
         assert (got == a[0]).all()
+        # the same with the row sweeps streamed between the bands (tagged mailboxes) and the column sweeps on their own stream
+        from sister_b200.bands import connect_row_mailboxes_in_process
+        connect_row_mailboxes_in_process(workers)
+        for _ in range(2):
+            rows = run_bands_in_process(workers)
+            got = np.concatenate([as_uint16(r) for r in rows], axis=0)
+            assert (got == a[0]).all()
 # a frame wide enough (264 x 256 padded) for the chunked median kernel, small D
 w2, h2, D2 = 248, 240, 8
 views2 = make_rig(w2, h2, D2, seed=43, channels=1)

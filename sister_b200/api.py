@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "sister_submit_device", "sister_sync", "sister_dev_alloc", "sister_dev_free", "sister_dev_memset", "sister_ipc_export", "sister_ipc_open", "sister_ipc_close", "sister_host_alloc", "sister_host_free", "sister_dev_upload",
     "sister_dev_download", "sister_set_profiling", "sister_region_begin", "sister_region_end", "sister_get_stage_ms", "sister_get_stage_launches",
     "sister_get_launch_count", "sister_debug_fetch", "sister_set_test_taps", "sister_set_full_frame",
-    "sister_stereo", "sister_create_band", "sister_band_state_bytes", "sister_band_submit", "sister_band_share_bytes", "sister_band_submit_share", "sister_band_submit_rest", "sister_band_rows", "sister_band_columns", "sister_band_vertical", "sister_band_finish", "sister_test_sgm", "sister_strerror", "sister_last_error",
+    "sister_stereo", "sister_create_band", "sister_band_state_bytes", "sister_band_submit", "sister_band_share_bytes", "sister_band_submit_share", "sister_band_submit_rest", "sister_band_rows", "sister_band_columns", "sister_band_columns_wait", "sister_band_vertical", "sister_band_finish", "sister_test_sgm", "sister_strerror", "sister_last_error",
     "sister_version",
 )
 
@@ -133,6 +133,8 @@ def load_library():
     L.sister_band_rows.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_uint]
     L.sister_band_columns.restype = C.c_int
     L.sister_band_columns.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.sister_band_columns_wait.restype = C.c_int
+    L.sister_band_columns_wait.argtypes = [vp, C.c_int]
     L.sister_band_vertical.restype = C.c_int
     L.sister_band_vertical.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.sister_band_finish.restype = C.c_int
@@ -362,6 +364,9 @@ class Engine:
     def band_columns(self, slot: int, pass_: int, state_in_ptr: int, state_out_ptr: int):
         self._chk(self.lib.sister_band_columns(self.ctx, slot, pass_, C.c_void_p(state_in_ptr) if state_in_ptr else None,
                                                C.c_void_p(state_out_ptr) if state_out_ptr else None))
+
+    def band_columns_wait(self, slot: int):
+        self._chk(self.lib.sister_band_columns_wait(self.ctx, slot))
 
     def band_vertical(self, slot: int, pass_: int, state_in_ptr: int, state_out_ptr: int):
         self._chk(self.lib.sister_band_vertical(self.ctx, slot, pass_, C.c_void_p(state_in_ptr) if state_in_ptr else None,

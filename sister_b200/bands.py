@@ -301,8 +301,8 @@ class EngineBandWorker:
             self.torch.cuda.current_stream().synchronize()
         self.eng.band_columns(self.slot, p, state_in.data_ptr() if state_in is not None else 0, out.data_ptr() if want_out else 0)
         if want_out:
-            self.eng.sync(self.slot)
-        return out
+            self.eng.band_columns_wait(self.slot)  # the state must be complete before it is sent (the row sweeps, on the slot's
+        return out                                 # main stream, are not waited for)
 
     def vertical(self, p: int, state_in, want_out: bool):
         out = self.new_state() if want_out else None
@@ -315,6 +315,7 @@ class EngineBandWorker:
 
     def drain(self):
         self.eng.sync(self.slot)
+        self.eng.band_columns_wait(self.slot)
         self.torch.cuda.synchronize()
 
     def finish(self):

@@ -37,6 +37,11 @@ struct Slot {
     bool busy = false, host_io = false;
     bool full_frame = false; // the last run aggregated the whole padded frame (raw_disp is complete)
     int band_r0 = 0, band_r1 = 0; // row band in progress (sister_band_*)
+    // column sweeps of a band beside its streamed row sweeps (sister_band_columns): their own stream and mailbox, made on first use
+    cudaStream_t st_cols = nullptr;
+    SgmScratch sgm_cols;
+    cudaEvent_t ev_fused = nullptr, ev_cols = nullptr; // the band's fused cost is ready (on st) / the column sweeps so far are done (on st_cols)
+    bool cols_pending = false;
     // profiling
     std::vector<cudaEvent_t> ev_b, ev_e;
     std::vector<int> ev_stage;
@@ -207,6 +212,10 @@ void free_slot(Slot &s)
     for (auto e : s.ev_b) cudaEventDestroy(e);
     for (auto e : s.ev_e) cudaEventDestroy(e);
     if (s.st) cudaStreamDestroy(s.st);
+    if (s.st_cols) cudaStreamDestroy(s.st_cols);
+    if (s.ev_fused) cudaEventDestroy(s.ev_fused);
+    if (s.ev_cols) cudaEventDestroy(s.ev_cols);
+    cudaFree(s.sgm_cols.mailbox);
     s = Slot();
 }
 
@@ -520,6 +529,8 @@ static int band_rest(sister_ctx *ctx, Slot &s)
     s.sgm.row_shift = ctx->band_rows > 0 ? (size_t)s.band_r0 * (size_t)d.Wp * (size_t)d.D : 0;
     launch_fuse(s.d_census, s.d_masks, d, vm, s.d_fused - s.sgm.row_shift, s.d_status, s.st, ctx->lc, s.band_r0, s.band_r1);
     s.last_fused = s.d_fused;
+    if (s.ev_fused) SCK(cudaEventRecord(s.ev_fused, s.st));
+    s.cols_pending = false;
     SCK(cudaGetLastError());
     SCK(take_launch_error(ctx));
     return SISTER_OK;
@@ -641,9 +652,36 @@ int sister_band_columns(sister_ctx *ctx, int slot, int pass, const uint8_t *stat
     const bool last_of_pass = pass == 0 ? s.band_r1 == s.dims.Hp : s.band_r0 == 0;
     if (!first_of_pass && !state_in_dev) { ctx->err = "state_in_dev is NULL but the band is not the first of this pass"; return SISTER_E_ARG; }
     if (!last_of_pass && !state_out_dev) { ctx->err = "state_out_dev is NULL but the band is not the last of this pass"; return SISTER_E_ARG; }
-    launch_sgm_band(5 + pass, s.d_fused - s.sgm.row_shift, s.dims, s.band_r0, s.band_r1, state_in_dev, state_out_dev, s.sgm, nullptr, nullptr, s.d_status, s.st, ctx->lc);
+    // beside the row sweeps, not behind them: a stream and a mailbox of their own (the pair volumes are the slot's; the two
+    // launches write different ones)
+    if (!s.st_cols) {
+        SCK(cudaStreamCreateWithFlags(&s.st_cols, cudaStreamNonBlocking));
+        SCK(cudaEventCreateWithFlags(&s.ev_fused, cudaEventDisableTiming));
+        SCK(cudaEventCreateWithFlags(&s.ev_cols, cudaEventDisableTiming));
+        s.sgm_cols.mailbox_bytes = s.sgm.mailbox_bytes;
+        if (cudaMalloc((void **)&s.sgm_cols.mailbox, s.sgm_cols.mailbox_bytes) != cudaSuccess) { cudaGetLastError(); ctx->err = "no memory for the column sweeps' mailbox"; return SISTER_E_NOMEM; }
+        SCK(cudaEventRecord(s.ev_fused, s.st)); // (the first frame: everything enqueued on the slot's stream so far)
+    }
+    s.sgm_cols.vols = s.sgm.vols;
+    s.sgm_cols.vol_stride = s.sgm.vol_stride;
+    s.sgm_cols.row_shift = s.sgm.row_shift;
+    if (!s.cols_pending) SCK(cudaStreamWaitEvent(s.st_cols, s.ev_fused, 0));
+    launch_sgm_band(5 + pass, s.d_fused - s.sgm.row_shift, s.dims, s.band_r0, s.band_r1, state_in_dev, state_out_dev, s.sgm_cols, nullptr, nullptr, s.d_status,
+                    s.st_cols, ctx->lc);
+    SCK(cudaEventRecord(s.ev_cols, s.st_cols));
+    s.cols_pending = true;
     SCK(cudaGetLastError());
     SCK(take_launch_error(ctx));
+    return SISTER_OK;
+}
+
+int sister_band_columns_wait(sister_ctx *ctx, int slot)
+{
+    int rc = slot_ok(ctx, slot);
+    if (rc) return rc;
+    Slot &s = ctx->slots[slot];
+    SCK(cudaSetDevice(ctx->device));
+    if (s.st_cols) SCK(cudaStreamSynchronize(s.st_cols));
     return SISTER_OK;
 }
 
@@ -654,6 +692,7 @@ int sister_band_finish(sister_ctx *ctx, int slot, uint16_t *out_dev)
     Slot &s = ctx->slots[slot];
     if (!out_dev || s.band_r1 <= s.band_r0) { ctx->err = "sister_band_submit first; out_dev must not be null"; return SISTER_E_ARG; }
     SCK(cudaSetDevice(ctx->device));
+    if (s.cols_pending) { SCK(cudaStreamWaitEvent(s.st, s.ev_cols, 0)); s.cols_pending = false; }
     launch_sgm_band(3, s.d_fused - s.sgm.row_shift, s.dims, s.band_r0, s.band_r1, nullptr, nullptr, s.sgm, nullptr, out_dev, s.d_status, s.st, ctx->lc);
     SCK(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, s.st));
     SCK(cudaGetLastError());
