@@ -8,7 +8,6 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# SISTER_B200_LIB: measurement aid, an alternative build of the same library (A/B runs of kernel variants)
 _LIB_PATH = os.path.join(_HERE, "libsister_b200.so")
 
 MODE_MULTIVIEW, MODE_HORIZONTAL, MODE_VERTICAL, MODE_ALL = 1, 2, 4, 7
