@@ -47,7 +47,7 @@ namespace sister {
 
 // compute warps per block (+ 1 mailbox warp): up to 18 while a lane holds few registers of state, fewer for the long
 // disparity ranges, whose state needs the registers a smaller block leaves per thread
-__host__ __device__ constexpr int sweep_warps_max(int NR) { return NR <= 8 ? 20 : NR <= 12 ? 12 : 8; }
+__host__ __device__ constexpr int sweep_warps_max(int NR) { return NR <= 8 ? 20 : NR <= 12 ? 17 : 8; }
 constexpr int kSweepWarpsMin = 6;  // the mailbox allocation of a context is sized for this many (sgm_mailbox_bytes)
 constexpr int kRing = 8;           // cost ring slots per warp
 constexpr unsigned long long kWaitNs = 4000000000ull; // a hand-over that takes 4 s is a broken pipeline, not a slow one
