@@ -113,9 +113,9 @@ __device__ __forceinline__ uint32_t lds32(unsigned a) { uint32_t v; asm volatile
 __device__ __forceinline__ uint2 lds64v(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint4 lds128v(unsigned a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts64(unsigned a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};\n" ::"r"(a), "r"(x), "r"(y) : "memory"); }
-__device__ __forceinline__ uint32_t ld_relaxed(const uint8_t *p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_relaxed(uint8_t *p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
-// the same towards / from another GPU's memory (row sweeps streamed between row bands)
+// mailbox words: relaxed, never cached in L1. System scope because the same code hands the row sweeps' states to the GPU of the
+// neighbouring row band (peer memory); on local memory it costs the same as .gpu (measured), and one form keeps the mailbox
+// warp's step free of branches (a run-time choice between the two cost 3 % of the kernel)
 __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint8_t *p) { uint32_t v; asm volatile("ld.relaxed.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_relaxed_sys(uint8_t *p, uint32_t v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 // The step barrier of a block (compute warps + mailbox warp; warps without a role have left). Warps of different roles reach
@@ -383,7 +383,6 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
     unsigned dst_tag = 0u;
     if (b < g.nblk - 1) { dst = mailbox + (g.mb_off + (long long)b * T) * EB; dst_tag = tagword; }
     else if (g.row && g.band_out) { dst = g.band_out; dst_tag = g.band_tag; }
-    const bool src_sys = b == 0 && g.band_tag != 0u, dst_sys = b == g.nblk - 1 && g.band_tag != 0u;
     const long long lane_off = (long long)li.sl * 4;
     uint32_t a[NR];
     // entry 0 at the first step. A column sweep continued from the band before takes the predecessor of the block's first
@@ -406,7 +405,7 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
         if (imp && src && s < T - 1) {
             const uint8_t *e = src + (long long)s * EB + lane_off;
 #pragma unroll
-            for (int k = 0; k < NH; k++) w[k] = src_sys ? ld_relaxed_sys(e + (long long)k * LPC * 4) : ld_relaxed(e + (long long)k * LPC * 4);
+            for (int k = 0; k < NH; k++) w[k] = ld_relaxed_sys(e + (long long)k * LPC * 4);
         } else {
 #pragma unroll
             for (int k = 0; k < NH; k++) w[k] = src_tag;
@@ -428,8 +427,7 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
             uint8_t *e = dst + (long long)(s - 1) * EB + lane_off;
 #pragma unroll
             for (int k = 0; k < NH; k++) {
-                if (dst_sys) st_relaxed_sys(e + (long long)k * LPC * 4, w[k]);
-                else st_relaxed(e + (long long)k * LPC * 4, w[k]);
+                st_relaxed_sys(e + (long long)k * LPC * 4, w[k]);
             }
         }
         // ---- deliver the predecessor's state after step s for step s + 1 (read two entries ahead)
@@ -455,7 +453,7 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
                 if (imp) {
                     const uint8_t *e = src + (long long)s * EB + lane_off;
 #pragma unroll
-                    for (int k = 0; k < NH; k++) w[k] = src_sys ? ld_relaxed_sys(e + (long long)k * LPC * 4) : ld_relaxed(e + (long long)k * LPC * 4);
+                    for (int k = 0; k < NH; k++) w[k] = ld_relaxed_sys(e + (long long)k * LPC * 4);
                 }
             }
             if (imp) {
@@ -472,8 +470,7 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
         uint8_t *e = dst + (long long)(T - 1) * EB + lane_off;
 #pragma unroll
         for (int k = 0; k < NH; k++) {
-            if (dst_sys) st_relaxed_sys(e + (long long)k * LPC * 4, w[k]);
-            else st_relaxed(e + (long long)k * LPC * 4, w[k]);
+            st_relaxed_sys(e + (long long)k * LPC * 4, w[k]);
         }
     }
 }
