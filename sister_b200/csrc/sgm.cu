@@ -364,13 +364,15 @@ __device__ __forceinline__ void sweep_warp(const uint8_t *__restrict__ fused, ui
 // at the step's barrier. Entries are read two steps ahead so that the L2 round trip is off the step's critical path.
 template <int NR, int LPC, bool FULL>
 __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, const SweepGeo &g, int b, int ch, int last_e, uint8_t *__restrict__ mailbox, unsigned tagword,
-                                             unsigned x_s, int x_stride, int lane, int n_sync, int *__restrict__ status)
+                                             unsigned x_s, int x_stride, int lane, int n_sync, int *__restrict__ status, const int role)
 {
     constexpr int NH = NR / 2;
     constexpr int EX = NR * LPC * 4;
     constexpr long long EB = 2 * NR * LPC; // bytes of a mailbox / band entry
     const int T = g.t1 - g.t0;
-    const bool imp = lane < LPC, exp = lane >= LPC && lane < 2 * LPC;
+    // role 0: the importing warp, role 1: the exporting warp (one warp doing both spends a step on each in turn, and the mailbox
+    // warp's step is as long as a compute warp's)
+    const bool imp = role == 0 && lane < LPC, exp = role == 1 && lane >= LPC && lane < 2 * LPC;
     // where the predecessor's states come from, where the last chain's states go
     const uint8_t *src = nullptr;
     unsigned src_tag = 0u, src_mask = 0u;
@@ -383,6 +385,8 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
     unsigned dst_tag = 0u;
     if (b < g.nblk - 1) { dst = mailbox + (g.mb_off + (long long)b * T) * EB; dst_tag = tagword; }
     else if (g.row && g.band_out) { dst = g.band_out; dst_tag = g.band_tag; }
+    if (role == 0) dst = nullptr;
+    else src = nullptr;
     const long long lane_off = (long long)li.sl * 4;
     uint32_t a[NR];
     // entry 0 at the first step. A column sweep continued from the band before takes the predecessor of the block's first
@@ -476,7 +480,7 @@ __device__ __forceinline__ void mailbox_warp(const LaneInfo<NR, LPC, FULL> &li, 
 }
 
 template <int NR, int LPC, bool FULL, bool IL>
-__global__ void __launch_bounds__(NR <= 8 ? 1024 : (sweep_warps_max(NR) + 1) * 32) // (<= 64 registers: a block of another rig's match or fuse kernel fits beside a sweep block)
+__global__ void __launch_bounds__(NR <= 6 ? 1024 : NR <= 8 ? 896 : (sweep_warps_max(NR) + 2) * 32) // (<= 64 registers: a block of another rig's match or fuse kernel fits beside a sweep block)
     k_sgm_sweeps(const uint8_t *__restrict__ fused, Dims d, SweepPlan pl, uint8_t *__restrict__ vols, uint8_t *__restrict__ mailbox, int *__restrict__ status, unsigned one)
 {
     constexpr int CPW = 32 / LPC;
@@ -496,15 +500,15 @@ __global__ void __launch_bounds__(NR <= 8 ? 1024 : (sweep_warps_max(NR) + 1) * 3
     const int slots_left = g.n1 - g.n0 + g.lead - b * CH; // slots from this block's first to the sweep's last chain
     const int last_e = slots_left < CH ? slots_left : CH;
     const int n_live = (last_e + CPW - 1) / CPW;
-    const int n_sync = (n_live + 1) * 32;
+    const int n_sync = (n_live + 2) * 32;
     LaneInfo<NR, LPC, FULL> li;
     li.init(lane, d.D);
     opaque(li.up_mask); opaque(li.dn_mask);
     li.one = one; // a kernel argument: the only 1 neither nvvm nor ptxas can fold (add_fma)
     const unsigned x_s = (unsigned)__cvta_generic_to_shared(smem_raw);
     const int x_stride = (CH + 1) * EX;
-    if (warp == pl.nw_max) {
-        mailbox_warp<NR, LPC, FULL>(li, g, b, CH, last_e, mailbox, pl.tagword, x_s, x_stride, lane, n_sync, status);
+    if (warp >= pl.nw_max) {
+        mailbox_warp<NR, LPC, FULL>(li, g, b, CH, last_e, mailbox, pl.tagword, x_s, x_stride, lane, n_sync, status, warp - pl.nw_max);
         return;
     }
     if (warp >= n_live) return; // (also the warps between this sweep's nw and nw_max)
@@ -765,7 +769,7 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
     int nw[4] = {kWarpsMax, kWarpsMax, kWarpsMax, kWarpsMax};
     plan_sweeps(d, roi, b0, b1, mask, nw, pl); // chains and steps of every sweep (they do not depend on the block size)
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (kWarpsMax + 1) * 32, smem_for(kWarpsMax)) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (kWarpsMax + 2) * 32, smem_for(kWarpsMax)) != cudaSuccess || per_sm < 1) per_sm = 1;
     const long long capacity = (long long)per_sm * n_sm;
     long long best_cost = -1;
     for (int s0 = 0; s0 < 4; s0++) {
@@ -830,7 +834,7 @@ static void launch_sweeps_t(const uint8_t *fused, const Dims &d, const Roi &roi,
     const unsigned e = sc.epoch;
     pl.tagword = ((e & 1u) << 7) | (((e >> 1) & 1u) << 15) | (((e >> 2) & 1u) << 23) | (((e >> 3) & 1u) << 31);
     pl.vol_stride = sc.vol_stride ? (long long)sc.vol_stride : d.cells;
-    k_sgm_sweeps<NR, LPC, FULL, IL><<<(unsigned)pl.total_blocks, (pl.nw_max + 1) * 32, smem_for(pl.nw_max), st>>>(fused, d, pl, sc.vols - sc.row_shift, sc.mailbox, status, 1u);
+    k_sgm_sweeps<NR, LPC, FULL, IL><<<(unsigned)pl.total_blocks, (pl.nw_max + 2) * 32, smem_for(pl.nw_max), st>>>(fused, d, pl, sc.vols - sc.row_shift, sc.mailbox, status, 1u);
     lc.add();
 }
 
