@@ -117,8 +117,9 @@ __device__ __forceinline__ void match_block(unsigned c1_s, unsigned c2_s, unsign
     }
 }
 
-// grid (max(hv), 4), block 32 * min(ceil(max(wv) / (32 K)), 13), dynamic smem: 2 * wv u64 + wv u32; three blocks per SM
-__global__ void __launch_bounds__(416, 3) k_match_wta(const unsigned long long *__restrict__ census, Dims d, unsigned view_mask,
+// grid (max(hv) / shares, 4), block <= 224 threads (see launch_match_wta), dynamic smem: 2 * wv u64 + wv u32; five or more blocks per SM
+template <bool WIDE> // WIDE: rows too long for five blocks' worth of shared memory per SM -- three blocks of up to 13 warps
+__global__ void __launch_bounds__(WIDE ? 416 : 224, WIDE ? 3 : 5) k_match_wta(const unsigned long long *__restrict__ census, Dims d, unsigned view_mask,
                                                     int16_t *__restrict__ wtaL, int16_t *__restrict__ wtaR, int share, int n_shares)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -163,12 +164,21 @@ void launch_match_wta(const unsigned long long *census, const Dims &d, unsigned 
                       cudaStream_t st, LaunchCounter &lc, int share, int n_shares)
 {
     int m = d.Wp > d.Hp ? d.Wp : d.Hp;
-    size_t smem = (size_t)m * (8 + 8 + 4);
-    lc.fail(optin_dynamic_smem((const void *)k_match_wta, smem));
-    int warps = (m + 32 * kMatchK - 1) / (32 * kMatchK);
-    if (warps > 13) warps = 13;
+    const size_t smem = (size_t)m * (8 + 8 + 4);
+    // a row's column blocks (32 * kMatchK columns each) are dealt to at most 7 warps in as few equal rounds as possible: five
+    // or more small blocks per SM keep the POPC pipe busier through the blocks' load / store phases than three of 13 warps
+    // (0.936 -> 0.906 ms at c2) -- as long as five blocks' rows fit the SM's shared memory (frames up to ~2300 wide)
+    const int nblk = (m + 32 * kMatchK - 1) / (32 * kMatchK);
     dim3 grid((m + n_shares - 1) / n_shares, 4);
-    k_match_wta<<<grid, 32 * warps, smem, st>>>(census, d, view_mask, wtaL, wtaR, share, n_shares);
+    if (smem * 5 <= 220 * 1024) {
+        const int rounds = (nblk + 6) / 7, warps = (nblk + rounds - 1) / rounds;
+        lc.fail(optin_dynamic_smem((const void *)k_match_wta<false>, smem));
+        k_match_wta<false><<<grid, 32 * warps, smem, st>>>(census, d, view_mask, wtaL, wtaR, share, n_shares);
+    } else {
+        const int warps = nblk < 13 ? nblk : 13;
+        lc.fail(optin_dynamic_smem((const void *)k_match_wta<true>, smem));
+        k_match_wta<true><<<grid, 32 * warps, smem, st>>>(census, d, view_mask, wtaL, wtaR, share, n_shares);
+    }
     lc.add();
 }
 
