@@ -589,27 +589,56 @@ static void launch_median_chunks(const int16_t *wtaL, const int16_t *wtaR, const
     lc.add();
 }
 
-// grid (ceil(wv/256), max(hv), 4), block 256
+// grid (ceil(max(wv) / 32), ceil(max(hv) / 32), 4), block (32, 8): a 32 x 32 tile of the view frame. The masks live in the
+// image frame (hpp:203-252 un-flips / un-transposes them): for the two transposed views a tile's bytes go through shared
+// memory so that they, too, leave as runs of 32 consecutive bytes instead of one byte per image row.
 __global__ void __launch_bounds__(256) k_lrc_mask(const int16_t *__restrict__ medL, const int16_t *__restrict__ medR, Dims d,
                                                   unsigned view_mask, int16_t *__restrict__ lr_final, uint8_t *__restrict__ masks)
 {
-    const int v = blockIdx.z, r = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint8_t tile[32][36];
+    const int v = blockIdx.z, tx = threadIdx.x, ty = threadIdx.y;
     if (!((view_mask >> v) & 1u)) return;
     const int hv = view_rows(d, v), wv = view_cols(d, v);
-    if (r >= hv || c >= wv) return;
-    const size_t off = (size_t)v * d.px + (size_t)r * wv;
-    int b = medL[off + c];
-    if (b >= 0 && b <= c) { // postprocess.cpp:327
-        int mt = medR[off + c - b];
-        int diff = b - mt;
-        if (abs(diff) > kLrcThreshold) b = -10;
-    } else {
-        b = -10;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    if (r0 >= hv || c0 >= wv) return;
+    const int c = c0 + tx;
+#pragma unroll
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int r = r0 + rr;
+        uint8_t mk = 0;
+        if (r < hv && c < wv) {
+            const size_t off = (size_t)v * d.px + (size_t)r * wv;
+            int b = medL[off + c];
+            if (b >= 0 && b <= c) { // postprocess.cpp:327
+                int mt = medR[off + c - b];
+                int diff = b - mt;
+                if (abs(diff) > kLrcThreshold) b = -10;
+            } else {
+                b = -10;
+            }
+            lr_final[off + c] = (int16_t)b;
+            mk = !(b <= 0 || c < d.D); // hpp:203
+            if (v < 2) {
+                int i, j;
+                view_to_image(d, v, r, c, i, j);
+                masks[(size_t)v * d.px + (size_t)i * d.Wp + j] = mk;
+            }
+        }
+        tile[rr][tx] = mk;
     }
-    lr_final[off + c] = (int16_t)b;
-    int i, j;
-    view_to_image(d, v, r, c, i, j);
-    masks[(size_t)v * d.px + (size_t)i * d.Wp + j] = !(b <= 0 || c < d.D); // hpp:203
+    if (v < 2) return;
+    __syncthreads();
+    // one view column = one image row; the lanes take the tile's view rows = 32 consecutive image columns
+    const int r = r0 + tx;
+#pragma unroll
+    for (int cc = ty; cc < 32; cc += 8) {
+        const int cv = c0 + cc;
+        if (r < hv && cv < wv) {
+            int i, j;
+            view_to_image(d, v, r, cv, i, j);
+            masks[(size_t)v * d.px + (size_t)i * d.Wp + j] = tile[tx][cc];
+        }
+    }
 }
 
 void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims &d, unsigned view_mask, int16_t *medL,
@@ -629,8 +658,8 @@ void launch_median_lrc_mask(const int16_t *wtaL, const int16_t *wtaR, const Dims
         k_median<<<8, 1024, med_smem, st>>>(wtaL, wtaR, d, view_mask, medL, medR);
         lc.add();
     }
-    dim3 grid((m + 255) / 256, m, 4);
-    k_lrc_mask<<<grid, 256, 0, st>>>(medL, medR, d, view_mask, lr_final, masks);
+    dim3 grid((m + 31) / 32, (m + 31) / 32, 4);
+    k_lrc_mask<<<grid, dim3(32, 8), 0, st>>>(medL, medR, d, view_mask, lr_final, masks);
     lc.add();
 }
 
