@@ -188,7 +188,8 @@ int sister_band_vertical(sister_ctx *ctx, int slot, int pass, const uint8_t *sta
  *                        band has finished: a column sweep has only as many steps as the band has rows). It runs on a second
  *                        stream of the slot, beside the row sweeps; sister_band_columns_wait() blocks until the column sweeps
  *                        enqueued so far are done (state_out_dev complete) without waiting for the row sweeps, and
- *                        sister_band_finish orders the final sweep behind both.
+ *                        sister_band_finish orders the final sweep behind both. (The second stream has a hand-over mailbox of
+ *                        its own, allocated on the slot's first sister_band_columns call: as large as the slot's first one.)
  * The bands' sister_band_rows must all be enqueued before any of them is waited for; a band whose neighbour never starts
  * reports SISTER_E_INTERNAL (status bit "spin timeout") after a few seconds instead of hanging. */
 int sister_band_rows(sister_ctx *ctx, int slot, int passes, const uint8_t *in_pass0, uint8_t *out_pass0, const uint8_t *in_pass1,
