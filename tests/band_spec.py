@@ -57,3 +57,71 @@ class NumpyBandWorker:
             disp[:, jj] = S[:, j, : min(j, self.D - 1) + 1].argmin(axis=1)
         enc = np.minimum(disp * 255, 65535).astype(np.uint16)
         return torch.from_numpy(enc.view(np.int16))
+
+
+class StreamedNumpyBandWorker(NumpyBandWorker):
+    """The same band with the scalable schedule's interface (sister_b200/bands.py: share_match, stream_rows): the WTA share is
+    a token that is all-gathered, the row sweeps take their states from the neighbouring band through `mailboxes` -- a dict shared
+    by the workers of one process, or torch.distributed send / recv between ranks -- and only the column sweeps are left for
+    the two wavefronts. (numpy cannot run the bands' row sweeps at the same time; what is checked is the split of the state
+    and the order of the calls.)"""
+    share_match = True
+    stream_rows = True
+
+    def __init__(self, C, D, H, W, row0, row1, rank, world, mailboxes=None):
+        super().__init__(C, D, H, W, row0, row1)
+        self.rank, self.world, self.mailboxes = rank, world, mailboxes
+        self.calls = []
+
+    def submit_share(self, share, n_shares):
+        self.calls.append("share")
+        return torch.full((4,), share, dtype=torch.uint8)
+
+    def submit_rest(self, gathered, n_shares):
+        assert gathered.tolist() == [r for r in range(n_shares) for _ in range(4)]  # every rank's share, in share order
+        self.calls.append("rest")
+
+    def _row_sweep(self, p, st):
+        s = Sweep(2 * p, self.Hp, self.Wp, self.roi, (self.row0, self.row1))
+        out = np.zeros((self.Wp, self.D), np.int64)
+        if not s.empty:
+            ex = run_sweep(self.C, s, self.V[2 * p], None if st is None else st[: s.t1 - s.t0])
+            out[: len(ex)] = ex
+        return out
+
+    def rows(self, passes=3):
+        import torch.distributed as dist
+
+        self.calls.append(f"rows{passes}")
+        for p in (0, 1):
+            if not (passes >> p) & 1:
+                continue
+            src, dst = (self.rank - 1, self.rank + 1) if p == 0 else (self.rank + 1, self.rank - 1)
+            st = None
+            if 0 <= src < self.world:
+                if self.mailboxes is not None:
+                    st = self.mailboxes[(p, src)]
+                else:
+                    buf = torch.zeros(self.Wp * self.D, dtype=torch.uint8)
+                    dist.recv(buf, src=src)
+                    st = buf.numpy().reshape(self.Wp, self.D).astype(np.int64)
+            out = self._row_sweep(p, st)
+            if 0 <= dst < self.world:
+                if self.mailboxes is not None:
+                    self.mailboxes[(p, self.rank)] = out
+                else:
+                    dist.send(torch.from_numpy(out.astype(np.uint8).reshape(-1)), dst=dst)
+
+    def columns(self, p, state_in, want_out):
+        self.calls.append(f"columns{p}")
+        st = None if state_in is None else state_in.numpy().reshape(3, self.Wp, self.D).astype(np.int64)
+        out = np.zeros((3, self.Wp, self.D), np.int64)
+        s = Sweep(2 * p + 1, self.Hp, self.Wp, self.roi, (self.row0, self.row1))
+        if not s.empty:
+            n = s.n1 - s.n0
+            a, r = run_sweep(self.C, s, self.V[2 * p + 1], None if st is None else (st[1][:n], st[2][:n]))
+            out[1][:n], out[2][:n] = a, r
+        return torch.from_numpy(out.astype(np.uint8).reshape(-1)) if want_out else None
+
+    def vertical(self, p, state_in, want_out):
+        raise AssertionError("the streamed schedule must not fall back to sister_band_vertical")

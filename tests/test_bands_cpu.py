@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from band_spec import NumpyBandWorker  # noqa: E402
+from band_spec import NumpyBandWorker, StreamedNumpyBandWorker  # noqa: E402
 from sgm_spec import sgm_decomposed  # noqa: E402
 
 from sister_b200.bands import (band_program, band_rows, compute_banded, crop_rows_of_band, gather_band_rows, run_bands_in_process,  # noqa: E402
@@ -67,6 +67,52 @@ def test_band_decomposition_equals_whole_frame(world):
     rows = run_bands_in_process(workers)
     got = np.concatenate([r.numpy().view(np.uint16) for r in rows], axis=0)
     assert (got == whole_frame_map(C)).all()
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_streamed_schedule_in_process_equals_whole_frame(world):
+    """run_bands_in_process with share_match + stream_rows workers: the WTA shares are gathered, the row sweeps run producers
+    first (pass 0 top to bottom, pass 1 bottom to top), then the column sweeps alone go through the two wavefronts."""
+    C = fused()
+    boxes = {}
+    workers = [StreamedNumpyBandWorker(C, D, H, W, *band_rows(HP, world, r), r, world, boxes) for r in range(world)]
+    rows = run_bands_in_process(workers)
+    got = np.concatenate([r.numpy().view(np.uint16) for r in rows], axis=0)
+    assert (got == whole_frame_map(C)).all()
+    for w in workers:
+        assert w.calls[:4] == ["share", "rest", "rows1", "rows2"] and sorted(w.calls[4:]) == ["columns0", "columns1"]
+
+
+def _streamed_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w = StreamedNumpyBandWorker(fused(), D, H, W, *band_rows(HP, world, rank), rank, world)
+        rows = compute_banded(w, world, rank)
+        assert w.calls[:3] == ["share", "rest", "rows3"] and sorted(w.calls[3:]) == ["columns0", "columns1"]
+        full = gather_band_rows(rows, D, H, HP, dst=0)
+        if rank == 0:
+            q.put(full.numpy().view(np.uint16).copy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_ranks_with_the_streamed_schedule(world):
+    """compute_banded over gloo with share_match + stream_rows: all_gather_into_tensor of the shares, rows() once per rank, the
+    column states through band_program's blocking sends and receives."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_streamed_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert (got == whole_frame_map(fused())).all()
 
 
 def _worker(rank, world, port, q):
