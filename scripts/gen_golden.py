@@ -30,6 +30,9 @@ RIGS = [
     # true colour (B != G != R): the fixed-point BGR2GRAY of hpp:29-33 on what cv::imread hands over (compute_disp.cpp:19-23)
     ("rig_96x64_d32_colour", 96, 64, 32, 1240, "smooth", True),
     ("rig_80x72_d24_colour", 80, 72, 24, 1241, "smooth", True),
+    # padded 264 x 256: wide enough for the chunked median kernel (two full chunks + a last chunk of two lanes one way, exactly
+    # two chunks the other way); small D keeps the fixture small
+    ("rig_248x240_d8", 248, 240, 8, 1242, "smooth", False),
 ]
 
 
